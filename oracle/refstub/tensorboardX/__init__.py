@@ -1,0 +1,9 @@
+class SummaryWriter:
+    def __init__(self, *a, **k):
+        pass
+
+    def add_scalar(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
