@@ -1,0 +1,100 @@
+/* sympa_b200 - C ABI of the B200-native Siegel / SPD pair-distance hot path.
+ *
+ * Drop-in boundary for the one hot path of fedelopez77/sympa: everything the reference does
+ * between `Model.forward` gathering two embedding rows and the embedding gradient being ready
+ * for the optimizer.  All pointers are DEVICE pointers (caller allocates everything, the library
+ * never allocates, frees or retains a pointer past the call), `stream` is a cudaStream_t passed as
+ * void*, every call is asynchronous on that stream and returns an int status (0 = ok) for argument
+ * errors only; numerical domain problems are OR-ed into the caller's device `status` word
+ * (SYMPA_STATUS_* bits) instead of the reference's host-synchronising asserts
+ * (sympa/manifolds/siegel_manifold.py:65-66).
+ *
+ * Layouts (sympa/math/csym_math.py:1-8, sympa/embeddings.py:59-68):
+ *   complex symmetric point  (2, n, n) float64, [0] real part, [1] imaginary part, row-major
+ *   spd point                (n, n)    float64
+ *   table                    (num_rows, 2, n, n) / (num_rows, n, n), contiguous
+ *   idx                      (num_pairs, 2) int64: (src row, dst row)   (train.py:95)
+ *   vvd                      (num_pairs, n) ascending vector-valued distance
+ *
+ * The reference-side binding is a ctypes stub - see INTEGRATION.md.
+ */
+#ifndef SYMPA_B200_H_
+#define SYMPA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYMPA_ABI_VERSION 1
+
+/* manifold kinds: sympa/embeddings.py:144-149 ("upper", "bounded") and :142 ("spd") */
+enum { SYMPA_KIND_UPPER = 0, SYMPA_KIND_BOUNDED = 1, SYMPA_KIND_SPD = 2 };
+/* sympa/manifolds/metrics.py:6-12 */
+enum { SYMPA_METRIC_RIEM = 0, SYMPA_METRIC_FONE = 1, SYMPA_METRIC_FINF = 2, SYMPA_METRIC_FMIN = 3, SYMPA_METRIC_WSUM = 4 };
+
+/* return codes */
+enum {
+  SYMPA_OK = 0,
+  SYMPA_ERR_BAD_ARG = 1,      /* null / inconsistent pointers, negative sizes */
+  SYMPA_ERR_UNSUPPORTED = 2,  /* n outside [1, SYMPA_MAX_N], unknown kind / metric */
+  SYMPA_ERR_CUDA = 3          /* launch failed; see sympa_last_cuda_error() */
+};
+#define SYMPA_MAX_N 10
+
+/* bits of the device status word */
+#define SYMPA_STATUS_NOT_PD 1u            /* a point is outside the manifold (Cholesky pivot <= 0) */
+#define SYMPA_STATUS_TAKAGI_ABOVE_ONE 2u  /* siegel_manifold.py:66 assert */
+#define SYMPA_STATUS_NO_CONVERGE 4u       /* Jacobi sweep cap reached */
+#define SYMPA_STATUS_NON_FINITE 8u
+#define SYMPA_STATUS_BAD_INDEX 16u        /* idx outside [0, num_rows) - the pair is skipped */
+
+int sympa_version(void);
+const char* sympa_error_string(int code);
+const char* sympa_last_cuda_error(void);
+
+/* bytes of `saved_state` that sympa_dist_forward needs to make a later sympa_dist_backward possible:
+ * the per-pair unit gradients d dist / d z1, d dist / d z2, i.e. 2 * num_pairs * point_doubles * 8. */
+int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs);
+
+/* Forward of manifold.dist (siegel_manifold.py:41-72, bounded_domain.py:27-39, geoopt spd dist).
+ * Operands come either materialised (z1, z2: (num_pairs, point)) or as a fused gather
+ * (table + idx; replaces Embeddings.forward, sympa/embeddings.py:29-34).  Exactly one of the two
+ * forms must be given.  wsum_w: n doubles (metrics.py:108) when metric == WSUM.
+ * dist_out (num_pairs) is required; vvd_out (num_pairs, n) and status are optional.
+ * saved_state == NULL -> forward only (evaluation, runner.py:124-154). */
+int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs,
+                       const double* z1, const double* z2,
+                       const double* table, int64_t num_rows, const int64_t* idx,
+                       const double* wsum_w,
+                       double* dist_out, double* vvd_out, double* saved_state,
+                       unsigned int* status, void* stream);
+
+/* Backward: replaces autograd through the ~250 torch ops of dist plus the gather backward.
+ * grad_dist (num_pairs) is dL/d dist.  Materialised form: grad_z1 / grad_z2 are OVERWRITTEN with
+ * the (symmetric) gradients.  Table form: grad_table (num_rows, point) is ACCUMULATED into with
+ * FP64 atomics (caller zeroes it, as zero_grad does at runner.py:95-96).  For metric WSUM pass vvd
+ * and wsum_w to have dL/dw accumulated into grad_wsum_w (n doubles). */
+int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs,
+                        const double* grad_dist, const double* saved_state,
+                        double* grad_z1, double* grad_z2,
+                        double* grad_table, int64_t num_rows, const int64_t* idx,
+                        const double* vvd, const double* wsum_w, double* grad_wsum_w,
+                        void* stream);
+
+/* One fused launch for a training step of the distortion objective (sympa/losses.py:16-19 with
+ * the scale of sympa/model.py:30):   L = sum_p | (scale * dist_p / graph_dist_p)^2 - 1 |.
+ * Gathers both rows, computes dist, the loss term and its derivative, and scatter-adds
+ * dL/d table into grad_table.  loss_out, grad_scale (1 double each), grad_wsum_w (n) and grad_table
+ * are ACCUMULATED into; dist_out (num_pairs) is optional. */
+int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs,
+                          const double* table, int64_t num_rows, const int64_t* idx,
+                          const double* graph_dist, double scale, const double* wsum_w,
+                          double* grad_table, double* grad_wsum_w, double* grad_scale, double* loss_out,
+                          double* dist_out, unsigned int* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYMPA_B200_H_ */

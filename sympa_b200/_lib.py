@@ -1,0 +1,70 @@
+"""ctypes binding of libsympa_b200.so (the C ABI of include/sympa_b200.h).  Fails loudly when the
+library is missing - there is no fallback path."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsympa_b200.so")
+
+KIND = {"upper": 0, "bounded": 1, "spd": 2}
+METRIC = {"riem": 0, "fone": 1, "finf": 2, "fmin": 3, "wsum": 4}
+MAX_N = 10
+
+STATUS_BITS = {
+    1: "a point is outside the manifold (Cholesky pivot <= 0)",
+    2: "a Takagi value exceeded 1.01 (reference assert siegel_manifold.py:66)",
+    4: "Jacobi sweep cap reached",
+    8: "non-finite distance",
+    16: "table index out of range",
+}
+
+EXPORTS = (
+    "sympa_version",
+    "sympa_error_string",
+    "sympa_last_cuda_error",
+    "sympa_workspace_bytes",
+    "sympa_dist_forward",
+    "sympa_dist_backward",
+    "sympa_distortion_step",
+)
+
+_lib = None
+
+
+class SympaLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SympaLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m sympa_b200.build` "
+            "(or __graft_entry__.build()); sympa_b200 has no CPU / eager fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    P, I, L, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    lib.sympa_version.restype = I
+    lib.sympa_error_string.restype = ctypes.c_char_p
+    lib.sympa_error_string.argtypes = [I]
+    lib.sympa_last_cuda_error.restype = ctypes.c_char_p
+    lib.sympa_workspace_bytes.restype = L
+    lib.sympa_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_dist_forward.restype = I
+    lib.sympa_dist_forward.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, P, P]
+    lib.sympa_dist_backward.restype = I
+    lib.sympa_dist_backward.argtypes = [I, I, I, L, P, P, P, P, P, L, P, P, P, P, P]
+    lib.sympa_distortion_step.restype = I
+    lib.sympa_distortion_step.argtypes = [I, I, I, L, P, L, P, P, D, P, P, P, P, P, P, P, P]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        lib = load()
+        msg = lib.sympa_error_string(rc).decode()
+        if rc == 3:
+            msg += ": " + lib.sympa_last_cuda_error().decode()
+        raise RuntimeError(f"sympa_b200: {msg} (code {rc})")

@@ -1,0 +1,271 @@
+// One-pair-per-thread kernels: gather -> dist (-> unit gradients | -> loss + scatter-add).
+// Instantiated per matrix size N in pair_kernels_n.cu (one translation unit per N so the build
+// parallelises); the C ABI in sympa_b200.cu dispatches through launch_pairs<N>().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pair_math.cuh"
+
+namespace sympa {
+
+enum Mode { kModeFwd = 0, kModeFwdSave = 1, kModeStep = 2 };
+
+struct PairArgs {
+  int64_t num_pairs;
+  const double* z1;
+  const double* z2;
+  const double* table;
+  int64_t num_rows;
+  const int64_t* idx;
+  const double* wsum_w;
+  double* dist_out;
+  double* vvd_out;
+  double* gz1;  // saved_state, first half : d dist / d z1, (num_pairs, point)
+  double* gz2;  // saved_state, second half: d dist / d z2
+  unsigned int* status;
+  int metric;
+  // fused distortion step
+  const double* graph_dist;
+  double scale;
+  double* grad_table;
+  double* grad_wsum_w;
+  double* grad_scale;
+  double* loss_out;
+};
+
+// launch the pair kernel for matrix size N; defined (explicitly instantiated) in pair_kernels_n.cu
+template <int N>
+int launch_pairs(int kind, int mode, const PairArgs& a, cudaStream_t stream);
+
+int check_launch();
+int grid_for(int64_t work_items, int threads, int waves_cap);
+
+#ifdef SYMPA_PAIR_KERNELS_IMPL
+
+constexpr int kThreads = 128;
+
+// namespace switch: reg = unrolled / registers (N <= SY_REG_MAX_N), loc = rolled / local memory
+template <bool REG>
+struct Math;
+template <>
+struct Math<true> {
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double upper(A... a) { return reg::upper_pair<N, G>(a...); }
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double bounded(A... a) { return reg::bounded_pair<N, G>(a...); }
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double spd(A... a) { return reg::spd_pair<N, G>(a...); }
+};
+template <>
+struct Math<false> {
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double upper(A... a) { return loc::upper_pair<N, G>(a...); }
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double bounded(A... a) { return loc::bounded_pair<N, G>(a...); }
+  template <int N, bool G, class... A>
+  static __device__ __forceinline__ double spd(A... a) { return loc::spd_pair<N, G>(a...); }
+};
+
+// one symmetric n x n block from global memory -> packed lower triangle, symmetrised
+template <int N, bool REG>
+__device__ __forceinline__ void load_packed(const double* __restrict__ p, double* s) {
+  if (REG) {
+    double buf[N * N];
+    if ((N * N) % 2 == 0) {
+      const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+      for (int i = 0; i < N * N / 2; ++i) {
+        const double2 t = __ldg(p2 + i);
+        buf[2 * i] = t.x;
+        buf[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) buf[i] = __ldg(p + i);
+    }
+    reg::pack_sym<N>(buf, s);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j <= i; ++j) s[tri(i, j)] = 0.5 * (__ldg(p + i * N + j) + __ldg(p + j * N + i));
+  }
+}
+
+// packed symmetric -> full n x n block in global memory
+template <int N, bool REG>
+__device__ __forceinline__ void store_full(double* __restrict__ out, const double* s) {
+  if (REG && (N * N) % 2 == 0) {
+    double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+    for (int e = 0; e < N * N / 2; ++e) {
+      const int i0 = (2 * e) / N, j0 = (2 * e) % N, i1 = (2 * e + 1) / N, j1 = (2 * e + 1) % N;
+      o2[e] = make_double2(s[tri(i0, j0)], s[tri(i1, j1)]);
+    }
+  } else if (REG) {
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) out[e] = s[tri(e / N, e % N)];
+  } else {
+#pragma unroll 1
+    for (int e = 0; e < N * N; ++e) out[e] = s[tri(e / N, e % N)];
+  }
+}
+
+template <int N, bool REG>
+__device__ __forceinline__ void atomic_add_full(double* __restrict__ out, const double* s, double scale) {
+  if (REG) {
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) atomicAdd(out + e, scale * s[tri(e / N, e % N)]);
+  } else {
+#pragma unroll 1
+    for (int e = 0; e < N * N; ++e) atomicAdd(out + e, scale * s[tri(e / N, e % N)]);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int N, int KIND, int MODE>
+__global__ void __launch_bounds__(kThreads) pair_kernel(const PairArgs a) {
+  constexpr bool REG = N <= SY_REG_MAX_N;
+  constexpr int T = Cfg<N>::kTri;
+  constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;
+  constexpr bool GRAD = MODE != kModeFwd;
+  using M = Math<REG>;
+  unsigned st = 0;
+  double loss_acc = 0.0, gscale_acc = 0.0;
+  double gw_acc[(MODE == kModeStep) ? N : 1];
+  if (MODE == kModeStep) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) gw_acc[k] = 0.0;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.num_pairs; p += stride) {
+    const double* p1;
+    const double* p2;
+    int64_t i1 = 0, i2 = 0;
+    if (a.idx != nullptr) {
+      const longlong2 ij = __ldg(reinterpret_cast<const longlong2*>(a.idx) + p);
+      i1 = ij.x;
+      i2 = ij.y;
+      if (i1 < 0 || i1 >= a.num_rows || i2 < 0 || i2 >= a.num_rows) {
+        st |= kStatusBadIndex;
+        if (a.dist_out) a.dist_out[p] = 0.0;
+        continue;
+      }
+      p1 = a.table + i1 * PER;
+      p2 = a.table + i2 * PER;
+    } else {
+      p1 = a.z1 + p * PER;
+      p2 = a.z2 + p * PER;
+    }
+    double vs[N];
+    double dist;
+    double g1r[GRAD ? T : 1], g1i[GRAD ? T : 1], g2r[GRAD ? T : 1], g2i[GRAD ? T : 1];
+    if (KIND == kSpd) {
+      double x[T], y[T];
+      load_packed<N, REG>(p1, x);
+      load_packed<N, REG>(p2, y);
+      dist = M::template spd<N, GRAD>(x, y, vs, g1r, g2r, &st);
+    } else {
+      double x1[T], y1[T], x2[T], y2[T];
+      load_packed<N, REG>(p1, x1);
+      load_packed<N, REG>(p1 + N * N, y1);
+      load_packed<N, REG>(p2, x2);
+      load_packed<N, REG>(p2 + N * N, y2);
+      if (KIND == kUpper)
+        dist = M::template upper<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &st);
+      else
+        dist = M::template bounded<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &st);
+    }
+    if (a.dist_out) a.dist_out[p] = dist;
+    if (a.vvd_out) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) a.vvd_out[p * N + k] = vs[k];
+    }
+    if (MODE == kModeFwdSave) {
+      double* o1 = a.gz1 + p * PER;
+      double* o2 = a.gz2 + p * PER;
+      store_full<N, REG>(o1, g1r);
+      store_full<N, REG>(o2, g2r);
+      if (KIND != kSpd) {
+        store_full<N, REG>(o1 + N * N, g1i);
+        store_full<N, REG>(o2 + N * N, g2i);
+      }
+    }
+    if (MODE == kModeStep) {
+      // L_p = |(s d / g)^2 - 1|   (sympa/losses.py:16-19 with the scale of sympa/model.py:30)
+      const double gd = __ldg(a.graph_dist + p);
+      const double r = a.scale * dist / gd;
+      const double e = r * r - 1.0;
+      loss_acc += fabs(e);
+      const double sg = e > 0.0 ? 1.0 : (e < 0.0 ? -1.0 : 0.0);  // torch.abs backward: sign, 0 at 0
+      const double dl_dr = sg * 2.0 * r;
+      const double dl_dd = dl_dr * a.scale / gd;
+      gscale_acc += dl_dr * dist / gd;
+      if (a.grad_wsum_w != nullptr && a.metric == kWsum) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) gw_acc[k] += (a.wsum_w[k] > 0.0) ? dl_dd * vs[k] : 0.0;
+      }
+      double* o1 = a.grad_table + i1 * PER;
+      double* o2 = a.grad_table + i2 * PER;
+      atomic_add_full<N, REG>(o1, g1r, dl_dd);
+      atomic_add_full<N, REG>(o2, g2r, dl_dd);
+      if (KIND != kSpd) {
+        atomic_add_full<N, REG>(o1 + N * N, g1i, dl_dd);
+        atomic_add_full<N, REG>(o2 + N * N, g2i, dl_dd);
+      }
+    }
+  }
+  if (MODE == kModeStep) {
+    loss_acc = warp_sum(loss_acc);
+    gscale_acc = warp_sum(gscale_acc);
+    if ((threadIdx.x & 31) == 0) {
+      if (a.loss_out) atomicAdd(a.loss_out, loss_acc);
+      if (a.grad_scale) atomicAdd(a.grad_scale, gscale_acc);
+    }
+    if (a.grad_wsum_w != nullptr && a.metric == kWsum) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double v = warp_sum(gw_acc[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.grad_wsum_w + k, v);
+      }
+    }
+  }
+  if (st != 0 && a.status != nullptr) atomicOr(a.status, st);
+}
+
+template <int N, int KIND, int MODE>
+static int launch_one(const PairArgs& a, cudaStream_t s) {
+  // grid-stride launch sized in whole waves of the SM count
+  const int grid = grid_for(a.num_pairs, kThreads, 16);
+  pair_kernel<N, KIND, MODE><<<grid, kThreads, 0, s>>>(a);
+  return check_launch();
+}
+
+template <int N, int KIND>
+static int launch_mode(int mode, const PairArgs& a, cudaStream_t s) {
+  switch (mode) {
+    case kModeFwd: return launch_one<N, KIND, kModeFwd>(a, s);
+    case kModeFwdSave: return launch_one<N, KIND, kModeFwdSave>(a, s);
+    case kModeStep: return launch_one<N, KIND, kModeStep>(a, s);
+  }
+  return 1;
+}
+
+template <int N>
+int launch_pairs(int kind, int mode, const PairArgs& a, cudaStream_t s) {
+  switch (kind) {
+    case kUpper: return launch_mode<N, kUpper>(mode, a, s);
+    case kBounded: return launch_mode<N, kBounded>(mode, a, s);
+    case kSpd: return launch_mode<N, kSpd>(mode, a, s);
+  }
+  return 2;
+}
+
+#endif  // SYMPA_PAIR_KERNELS_IMPL
+
+}  // namespace sympa

@@ -1,0 +1,266 @@
+// sympa_b200 - the C ABI declared in include/sympa_b200.h plus the element-wise backward kernels.
+//
+//   pair_kernel<N, KIND, MODE>   (pair_kernels.cuh)  gather -> dist (-> unit gradients | -> loss + scatter-add)
+//   scale_kernel                 grad_z = grad_dist[p] * unit gradient           (materialised backward)
+//   scatter_kernel               grad_table[idx] += grad_dist[p] * unit gradient (gather backward,
+//                                replaces the dense index_put of sympa/embeddings.py:34's backward)
+//   wsum_grad_kernel             dL/dw of the learnable wsum metric (sympa/manifolds/metrics.py:103-121)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sympa_b200.h"
+#include "pair_kernels.cuh"
+
+namespace sympa {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grad_z[p, :] = grad_dist[p] * unit[p, :]   (two operands in one launch)
+__global__ void __launch_bounds__(256) scale_kernel(int64_t total2, int per2, const double* __restrict__ gd,
+                                                    const double2* __restrict__ u1, const double2* __restrict__ u2,
+                                                    double2* __restrict__ o1, double2* __restrict__ o2) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total2; e += stride) {
+    const double g = __ldg(gd + e / per2);
+    double2 a = __ldg(u1 + e), b = __ldg(u2 + e);
+    o1[e] = make_double2(g * a.x, g * a.y);
+    o2[e] = make_double2(g * b.x, g * b.y);
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel1(int64_t total, int per, const double* __restrict__ gd,
+                                                     const double* __restrict__ u1, const double* __restrict__ u2,
+                                                     double* __restrict__ o1, double* __restrict__ o2) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const double g = __ldg(gd + e / per);
+    o1[e] = g * __ldg(u1 + e);
+    o2[e] = g * __ldg(u2 + e);
+  }
+}
+
+// grad_table[idx[p, s], :] += grad_dist[p] * unit_s[p, :]
+__global__ void __launch_bounds__(256) scatter_kernel(int64_t total, int per, int64_t num_rows,
+                                                      const double* __restrict__ gd, const int64_t* __restrict__ idx,
+                                                      const double* __restrict__ u1, const double* __restrict__ u2,
+                                                      double* __restrict__ grad_table) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t p = e / per;
+    const int c = (int)(e - p * per);
+    const double g = __ldg(gd + p);
+    const int64_t i1 = __ldg(idx + 2 * p), i2 = __ldg(idx + 2 * p + 1);
+    if (i1 < 0 || i1 >= num_rows || i2 < 0 || i2 >= num_rows) continue;
+    atomicAdd(grad_table + i1 * per + c, g * __ldg(u1 + e));
+    atomicAdd(grad_table + i2 * per + c, g * __ldg(u2 + e));
+  }
+}
+
+// grad_w[k] += sum_p grad_dist[p] * vvd[p, k] * (w_k > 0)      (relu backward, metrics.py:118)
+__global__ void __launch_bounds__(256) wsum_grad_kernel(int64_t num_pairs, int n, const double* __restrict__ gd,
+                                                        const double* __restrict__ vvd, const double* __restrict__ w,
+                                                        double* __restrict__ grad_w) {
+  double acc[SYMPA_MAX_N];
+#pragma unroll
+  for (int k = 0; k < SYMPA_MAX_N; ++k) acc[k] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < num_pairs; p += stride) {
+    const double g = __ldg(gd + p);
+#pragma unroll
+    for (int k = 0; k < SYMPA_MAX_N; ++k)
+      if (k < n) acc[k] += g * __ldg(vvd + p * n + k);
+  }
+#pragma unroll
+  for (int k = 0; k < SYMPA_MAX_N; ++k) {
+    if (k < n) {
+      double v = warp_sum_d(acc[k]);
+      if ((threadIdx.x & 31) == 0 && __ldg(w + k) > 0.0) atomicAdd(grad_w + k, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static thread_local char g_last_cuda_error[256] = "";
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(e));
+    return SYMPA_ERR_CUDA;
+  }
+  return SYMPA_OK;
+}
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+    cached = n;
+  }
+  return cached;
+}
+
+int grid_for(int64_t work_items, int threads, int waves_cap) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * waves_cap;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+#define SY_DECL(K) extern template int launch_pairs<K>(int, int, const PairArgs&, cudaStream_t);
+SY_DECL(1) SY_DECL(2) SY_DECL(3) SY_DECL(4) SY_DECL(5) SY_DECL(6) SY_DECL(7) SY_DECL(8) SY_DECL(9) SY_DECL(10)
+#undef SY_DECL
+
+static int launch_n(int n, int kind, int mode, const PairArgs& a, cudaStream_t s) {
+  switch (n) {
+#define SY_CASE(K) \
+  case K:          \
+    return launch_pairs<K>(kind, mode, a, s);
+    SY_CASE(1) SY_CASE(2) SY_CASE(3) SY_CASE(4) SY_CASE(5) SY_CASE(6) SY_CASE(7) SY_CASE(8) SY_CASE(9) SY_CASE(10)
+#undef SY_CASE
+  }
+  return SYMPA_ERR_UNSUPPORTED;
+}
+
+static bool valid_common(int kind, int n, int metric, int64_t num_pairs) {
+  return kind >= 0 && kind <= 2 && n >= 1 && n <= SYMPA_MAX_N && metric >= 0 && metric <= 4 && num_pairs >= 0;
+}
+
+static int point_doubles(int kind, int n) { return (kind == SYMPA_KIND_SPD ? 1 : 2) * n * n; }
+
+}  // namespace sympa
+
+using namespace sympa;
+
+extern "C" {
+
+int sympa_version(void) { return SYMPA_ABI_VERSION; }
+
+const char* sympa_error_string(int code) {
+  switch (code) {
+    case SYMPA_OK: return "ok";
+    case SYMPA_ERR_BAD_ARG: return "bad argument";
+    case SYMPA_ERR_UNSUPPORTED: return "unsupported kind / metric / matrix size";
+    case SYMPA_ERR_CUDA: return "CUDA error";
+  }
+  return "unknown";
+}
+
+const char* sympa_last_cuda_error(void) { return g_last_cuda_error; }
+
+int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs) {
+  if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N || num_pairs < 0) return -1;
+  return 2 * num_pairs * (int64_t)point_doubles(kind, n) * (int64_t)sizeof(double);
+}
+
+int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs, const double* z1, const double* z2,
+                       const double* table, int64_t num_rows, const int64_t* idx, const double* wsum_w,
+                       double* dist_out, double* vvd_out, double* saved_state, unsigned int* status, void* stream) {
+  if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  const bool mat = z1 != nullptr || z2 != nullptr;
+  const bool tab = table != nullptr || idx != nullptr;
+  if (mat == tab) return SYMPA_ERR_BAD_ARG;
+  if (mat && (z1 == nullptr || z2 == nullptr)) return SYMPA_ERR_BAD_ARG;
+  if (tab && (table == nullptr || idx == nullptr || num_rows <= 0)) return SYMPA_ERR_BAD_ARG;
+  if (dist_out == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (metric == SYMPA_METRIC_WSUM && kind != SYMPA_KIND_SPD && wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  PairArgs a = {};
+  a.num_pairs = num_pairs;
+  a.z1 = z1;
+  a.z2 = z2;
+  a.table = table;
+  a.num_rows = num_rows;
+  a.idx = idx;
+  a.wsum_w = wsum_w;
+  a.dist_out = dist_out;
+  a.vvd_out = vvd_out;
+  a.status = status;
+  a.metric = metric;
+  if (saved_state != nullptr) {
+    a.gz1 = saved_state;
+    a.gz2 = saved_state + num_pairs * (int64_t)point_doubles(kind, n);
+  }
+  return launch_n(n, kind, saved_state != nullptr ? kModeFwdSave : kModeFwd, a, (cudaStream_t)stream);
+}
+
+int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const double* grad_dist,
+                        const double* saved_state, double* grad_z1, double* grad_z2, double* grad_table,
+                        int64_t num_rows, const int64_t* idx, const double* vvd, const double* wsum_w,
+                        double* grad_wsum_w, void* stream) {
+  if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (grad_dist == nullptr || saved_state == nullptr) return SYMPA_ERR_BAD_ARG;
+  const bool mat = grad_z1 != nullptr || grad_z2 != nullptr;
+  const bool tab = grad_table != nullptr;
+  if (mat && (grad_z1 == nullptr || grad_z2 == nullptr)) return SYMPA_ERR_BAD_ARG;
+  if (tab && (idx == nullptr || num_rows <= 0)) return SYMPA_ERR_BAD_ARG;
+  if (!mat && !tab && grad_wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (grad_wsum_w != nullptr && (vvd == nullptr || wsum_w == nullptr)) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int per = point_doubles(kind, n);
+  const double* u1 = saved_state;
+  const double* u2 = saved_state + num_pairs * (int64_t)per;
+  int rc = SYMPA_OK;
+  if (mat) {
+    if (per % 2 == 0) {
+      const int64_t total2 = num_pairs * (int64_t)(per / 2);
+      scale_kernel<<<grid_for(total2, 256, 32), 256, 0, s>>>(total2, per / 2, grad_dist, (const double2*)u1,
+                                                             (const double2*)u2, (double2*)grad_z1, (double2*)grad_z2);
+    } else {  // spd with odd n
+      const int64_t total = num_pairs * (int64_t)per;
+      scale_kernel1<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, grad_dist, u1, u2, grad_z1, grad_z2);
+    }
+    rc = check_launch();
+    if (rc) return rc;
+  }
+  if (tab) {
+    const int64_t total = num_pairs * (int64_t)per;
+    scatter_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, num_rows, grad_dist, idx, u1, u2, grad_table);
+    rc = check_launch();
+    if (rc) return rc;
+  }
+  if (grad_wsum_w != nullptr && metric == SYMPA_METRIC_WSUM) {
+    wsum_grad_kernel<<<grid_for(num_pairs, 256, 4), 256, 0, s>>>(num_pairs, n, grad_dist, vvd, wsum_w, grad_wsum_w);
+    rc = check_launch();
+  }
+  return rc;
+}
+
+int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs, const double* table, int64_t num_rows,
+                          const int64_t* idx, const double* graph_dist, double scale, const double* wsum_w,
+                          double* grad_table, double* grad_wsum_w, double* grad_scale, double* loss_out,
+                          double* dist_out, unsigned int* status, void* stream) {
+  if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (table == nullptr || idx == nullptr || graph_dist == nullptr || grad_table == nullptr || num_rows <= 0)
+    return SYMPA_ERR_BAD_ARG;
+  if (metric == SYMPA_METRIC_WSUM && kind != SYMPA_KIND_SPD && wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  PairArgs a = {};
+  a.num_pairs = num_pairs;
+  a.table = table;
+  a.num_rows = num_rows;
+  a.idx = idx;
+  a.wsum_w = wsum_w;
+  a.dist_out = dist_out;
+  a.status = status;
+  a.metric = metric;
+  a.graph_dist = graph_dist;
+  a.scale = scale;
+  a.grad_table = grad_table;
+  a.grad_wsum_w = grad_wsum_w;
+  a.grad_scale = grad_scale;
+  a.loss_out = loss_out;
+  return launch_n(n, kind, kModeStep, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

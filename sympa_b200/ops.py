@@ -1,0 +1,212 @@
+"""Host side of the hot path: torch.autograd Functions over the C ABI.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic of
+`dist` happens in libsympa_b200.so.  Tensors must be CUDA float64 and contiguous.
+"""
+import torch
+
+from . import _lib
+
+_status_words = {}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def status_word(device):
+    """Per-device uint32 word the kernels OR their SYMPA_STATUS_* bits into."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    w = _status_words.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=device)
+        _status_words[key] = w
+    return w
+
+
+def check_status(device=None, reset=True):
+    """Host-synchronising check of the device status word (call once per step / epoch; the
+    reference asserted synchronously inside every dist call, siegel_manifold.py:65-66)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    w = status_word(device)
+    v = int(w.item()) & 0xFFFFFFFF
+    if reset:
+        w.zero_()
+    if v:
+        reasons = [msg for bit, msg in _lib.STATUS_BITS.items() if v & bit]
+        raise AssertionError("sympa_b200 status 0x%x: %s" % (v, "; ".join(reasons)))
+    return v
+
+
+def _require(t, name, dtype=torch.float64):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"sympa_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"sympa_b200: {name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _point_shape(kind, n):
+    return (n, n) if kind == "spd" else (2, n, n)
+
+
+def _check_n(n):
+    if not 1 <= n <= _lib.MAX_N:
+        raise NotImplementedError(f"sympa_b200 supports matrix sizes 1..{_lib.MAX_N}, got {n}")
+
+
+def forward_raw(kind, metric, z1=None, z2=None, table=None, idx=None, wsum_w=None, want_grad=False,
+                want_vvd=True):
+    """One forward launch.  Returns (dist, vvd or None, saved_state or None)."""
+    lib = _lib.load()
+    if table is not None:
+        table = _require(table, "table")
+        idx = _require(idx, "idx", torch.int64)
+        if idx.dim() != 2 or idx.shape[1] != 2:
+            raise ValueError("idx must have shape (num_pairs, 2)")
+        n = table.shape[-1]
+        if tuple(table.shape[1:]) != _point_shape(kind, n):
+            raise ValueError(f"table must have shape (N, {_point_shape(kind, n)})")
+        b, dev = idx.shape[0], table.device
+    else:
+        z1 = _require(z1, "z1")
+        z2 = _require(z2, "z2")
+        if z1.shape != z2.shape:
+            raise ValueError("z1 and z2 must have the same shape")
+        n = z1.shape[-1]
+        if tuple(z1.shape[1:]) != _point_shape(kind, n):
+            raise ValueError(f"points must have shape (b, {_point_shape(kind, n)}), got {tuple(z1.shape)}")
+        b, dev = z1.shape[0], z1.device
+    _check_n(n)
+    if metric == "wsum" and kind != "spd":
+        wsum_w = _require(wsum_w, "wsum_w").reshape(-1)
+        if wsum_w.numel() != n:
+            raise ValueError("wsum weights must have n entries")
+    else:
+        wsum_w = None
+    with torch.cuda.device(dev):
+        dist = torch.empty(b, dtype=torch.float64, device=dev)
+        vvd = torch.empty(b, n, dtype=torch.float64, device=dev) if want_vvd else None
+        saved = None
+        if want_grad:
+            nbytes = lib.sympa_workspace_bytes(_lib.KIND[kind], n, b)
+            saved = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+        _lib.check(lib.sympa_dist_forward(
+            _lib.KIND[kind], n, _lib.METRIC[metric], b, _ptr(z1), _ptr(z2), _ptr(table),
+            0 if table is None else table.shape[0], _ptr(idx), _ptr(wsum_w), _ptr(dist), _ptr(vvd), _ptr(saved),
+            _ptr(status_word(dev)), _stream()))
+    return dist, vvd, saved
+
+
+class _DistFn(torch.autograd.Function):
+    """dist(z1, z2) on materialised (b, 2, n, n) / (b, n, n) operands - what the reference's
+    Model.distance calls (sympa/model.py:32-38)."""
+
+    @staticmethod
+    def forward(ctx, z1, z2, wsum_w, kind, metric):
+        need = any(ctx.needs_input_grad[:3])
+        dist, vvd, saved = forward_raw(kind, metric, z1=z1, z2=z2, wsum_w=wsum_w, want_grad=need)
+        ctx.kind, ctx.metric, ctx.shape = kind, metric, z1.shape
+        ctx.save_for_backward(saved, vvd, wsum_w if metric == "wsum" else None)
+        ctx.mark_non_differentiable(vvd)
+        return dist, vvd
+
+    @staticmethod
+    def backward(ctx, grad_dist, _grad_vvd):
+        saved, vvd, wsum_w = ctx.saved_tensors
+        lib = _lib.load()
+        grad_dist = _require(grad_dist, "grad_dist")
+        b, n = vvd.shape
+        dev = vvd.device
+        with torch.cuda.device(dev):
+            g1 = torch.empty(ctx.shape, dtype=torch.float64, device=dev)
+            g2 = torch.empty(ctx.shape, dtype=torch.float64, device=dev)
+            gw = None
+            w_flat = None
+            if wsum_w is not None and ctx.needs_input_grad[2]:
+                gw = torch.zeros(n, dtype=torch.float64, device=dev)
+                w_flat = wsum_w.contiguous().reshape(-1)
+            _lib.check(lib.sympa_dist_backward(
+                _lib.KIND[ctx.kind], n, _lib.METRIC[ctx.metric], b, _ptr(grad_dist), _ptr(saved), _ptr(g1), _ptr(g2),
+                None, 0, None, _ptr(vvd), _ptr(w_flat), _ptr(gw), _stream()))
+        if gw is not None:
+            gw = gw.reshape(wsum_w.shape)
+        return g1, g2, gw, None, None
+
+
+class _TableDistFn(torch.autograd.Function):
+    """dist(table[idx[:,0]], table[idx[:,1]]) with the gather fused into the forward kernel and the
+    gather backward (dense index_put in the reference, sympa/embeddings.py:29-34) fused into an
+    atomic scatter-add."""
+
+    @staticmethod
+    def forward(ctx, table, idx, wsum_w, kind, metric):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        dist, vvd, saved = forward_raw(kind, metric, table=table, idx=idx, wsum_w=wsum_w, want_grad=need)
+        ctx.kind, ctx.metric, ctx.tshape = kind, metric, table.shape
+        ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None)
+        ctx.mark_non_differentiable(vvd)
+        return dist, vvd
+
+    @staticmethod
+    def backward(ctx, grad_dist, _grad_vvd):
+        saved, vvd, idx, wsum_w = ctx.saved_tensors
+        lib = _lib.load()
+        grad_dist = _require(grad_dist, "grad_dist")
+        b, n = vvd.shape
+        dev = vvd.device
+        with torch.cuda.device(dev):
+            gt = torch.zeros(ctx.tshape, dtype=torch.float64, device=dev)
+            gw = None
+            w_flat = None
+            if wsum_w is not None and ctx.needs_input_grad[2]:
+                gw = torch.zeros(n, dtype=torch.float64, device=dev)
+                w_flat = wsum_w.contiguous().reshape(-1)
+            _lib.check(lib.sympa_dist_backward(
+                _lib.KIND[ctx.kind], n, _lib.METRIC[ctx.metric], b, _ptr(grad_dist), _ptr(saved), None, None,
+                _ptr(gt), ctx.tshape[0], _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat), _ptr(gw), _stream()))
+        if gw is not None:
+            gw = gw.reshape(wsum_w.shape)
+        return gt, None, gw, None, None
+
+
+def dist(kind, metric, z1, z2, wsum_w=None):
+    """Differentiable distance and (non-differentiable) ascending vector-valued distance."""
+    return _DistFn.apply(z1, z2, wsum_w, kind, metric)
+
+
+def table_dist(kind, metric, table, idx, wsum_w=None):
+    return _TableDistFn.apply(table, idx, wsum_w, kind, metric)
+
+
+def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsum_w=None, grad_wsum_w=None,
+                    grad_scale=None, loss_out=None, dist_out=None):
+    """Fused training step of the distortion objective: accumulates into grad_table (and
+    grad_wsum_w, grad_scale, loss_out when given).  Returns loss_out (a 1-element tensor)."""
+    lib = _lib.load()
+    table = _require(table, "table")
+    idx = _require(idx, "idx", torch.int64)
+    graph_dist = _require(graph_dist, "graph_dist")
+    n = table.shape[-1]
+    _check_n(n)
+    dev = table.device
+    if grad_table.shape != table.shape or not grad_table.is_contiguous():
+        raise ValueError("grad_table must be a contiguous tensor shaped like table")
+    if metric == "wsum" and kind != "spd":
+        wsum_w = _require(wsum_w, "wsum_w").reshape(-1)
+    else:
+        wsum_w = None
+    with torch.cuda.device(dev):
+        if loss_out is None:
+            loss_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        _lib.check(lib.sympa_distortion_step(
+            _lib.KIND[kind], n, _lib.METRIC[metric], idx.shape[0], _ptr(table), table.shape[0], _ptr(idx),
+            _ptr(graph_dist), float(scale), _ptr(wsum_w), _ptr(grad_table), _ptr(grad_wsum_w), _ptr(grad_scale),
+            _ptr(loss_out), _ptr(dist_out), _ptr(status_word(dev)), _stream()))
+    return loss_out

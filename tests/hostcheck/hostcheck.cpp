@@ -1,0 +1,78 @@
+// TEST INFRASTRUCTURE: compiles sympa_b200/csrc/pair_math.cuh for the HOST so that the exact
+// per-pair templates the CUDA kernels instantiate can be checked against the golden vectors on a
+// machine without a GPU (tests/test_hostcheck.py).  Never loaded by the product package.
+//   variant 0 = namespace sympa::reg (unrolled, what the kernels use for n <= 4)
+//   variant 1 = namespace sympa::loc (rolled loops, what the kernels use for n > 4)
+#include "../../sympa_b200/csrc/pair_math.cuh"
+
+using namespace sympa;
+
+#define HC_RUN(NS)                                                                                              \
+  template <int N>                                                                                              \
+  static void run_##NS(int kind, int metric, int64_t b, const double* z1, const double* z2, const double* w,    \
+                       int grad, double* dist, double* vvd, double* g1, double* g2, unsigned* status) {        \
+    constexpr int T = Cfg<N>::kTri;                                                                             \
+    const int per = (kind == kSpd ? 1 : 2) * N * N;                                                             \
+    for (int64_t p = 0; p < b; ++p) {                                                                           \
+      const double* a = z1 + p * per;                                                                           \
+      const double* c = z2 + p * per;                                                                           \
+      double vs[N];                                                                                             \
+      unsigned st = 0;                                                                                          \
+      double d;                                                                                                 \
+      double o1r[T], o1i[T], o2r[T], o2i[T];                                                                    \
+      if (kind == kSpd) {                                                                                       \
+        double x[T], y[T];                                                                                      \
+        NS::pack_sym<N>(a, x);                                                                                  \
+        NS::pack_sym<N>(c, y);                                                                                  \
+        d = grad ? NS::spd_pair<N, true>(x, y, vs, o1r, o2r, &st) : NS::spd_pair<N, false>(x, y, vs, o1r, o2r, &st); \
+      } else {                                                                                                  \
+        double x1[T], y1[T], x2[T], y2[T];                                                                      \
+        NS::pack_sym<N>(a, x1);                                                                                 \
+        NS::pack_sym<N>(a + N * N, y1);                                                                         \
+        NS::pack_sym<N>(c, x2);                                                                                 \
+        NS::pack_sym<N>(c + N * N, y2);                                                                         \
+        if (kind == kUpper)                                                                                     \
+          d = grad ? NS::upper_pair<N, true>(x1, y1, x2, y2, metric, w, vs, o1r, o1i, o2r, o2i, &st)            \
+                   : NS::upper_pair<N, false>(x1, y1, x2, y2, metric, w, vs, o1r, o1i, o2r, o2i, &st);          \
+        else                                                                                                    \
+          d = grad ? NS::bounded_pair<N, true>(x1, y1, x2, y2, metric, w, vs, o1r, o1i, o2r, o2i, &st)          \
+                   : NS::bounded_pair<N, false>(x1, y1, x2, y2, metric, w, vs, o1r, o1i, o2r, o2i, &st);        \
+      }                                                                                                         \
+      dist[p] = d;                                                                                              \
+      for (int k = 0; k < N; ++k) vvd[p * N + k] = vs[k];                                                       \
+      *status |= st;                                                                                            \
+      if (grad) {                                                                                               \
+        for (int i = 0; i < N; ++i)                                                                             \
+          for (int j = 0; j < N; ++j) {                                                                         \
+            g1[p * per + i * N + j] = o1r[tri(i, j)];                                                           \
+            g2[p * per + i * N + j] = o2r[tri(i, j)];                                                           \
+            if (kind != kSpd) {                                                                                 \
+              g1[p * per + N * N + i * N + j] = o1i[tri(i, j)];                                                 \
+              g2[p * per + N * N + i * N + j] = o2i[tri(i, j)];                                                 \
+            }                                                                                                   \
+          }                                                                                                     \
+      }                                                                                                         \
+    }                                                                                                           \
+  }
+
+HC_RUN(reg)
+HC_RUN(loc)
+
+extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b, const double* z1, const double* z2,
+                             const double* w, int grad, double* dist, double* vvd, double* g1, double* g2,
+                             unsigned* status) {
+  if (variant == 0) {
+    switch (n) {
+#define CASE(K) case K: run_reg<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
+      CASE(1) CASE(2) CASE(3) CASE(4)
+#undef CASE
+    }
+    return 1;
+  }
+  switch (n) {
+#define CASE(K) case K: run_loc<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+  }
+  return 1;
+}

@@ -1,0 +1,219 @@
+"""Parity of the CUDA path (through the C ABI / the manifold API) with the oracle and with the golden
+vectors of the unmodified reference.  Tolerances (BASELINE.json north_star):
+  dist / vvd:  1e-9 relative (float64)
+  gradients:   sym(grad) within 1e-6 max|g| for n <= 6, 1e-5 max|g| for n = 10 (the reference's own
+               autograd noise is 1e-10 .. 3e-6 there)."""
+import numpy as np
+import pytest
+import torch
+
+import siegel_oracle as so
+from conftest import METRICS, golden_files, grad_tolerance, load_golden, sym
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import sympa_b200
+    assert torch.cuda.is_available()
+    return sympa_b200
+
+
+def make_manifold(sb, kind, n, metric, w=None):
+    cls = {"upper": sb.UpperHalfManifold, "bounded": sb.BoundedDomainManifold}[kind]
+    man = cls(dims=n, metric=sb.MetricType.from_str(metric)).cuda()
+    if metric == "wsum":
+        man.metric.weights.data = torch.tensor(w, dtype=torch.float64, device="cuda").reshape(1, n)
+    return man
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_manifold_dist_matches_reference_golden(sb, path):
+    kind, n, regime, r = load_golden(path)
+    z1 = torch.tensor(r["z1"], device="cuda")
+    z2 = torch.tensor(r["z2"], device="cuda")
+    go = torch.tensor(r["go"], device="cuda")
+    for m in METRICS:
+        man = make_manifold(sb, kind, n, m, r.get("wsum_w"))
+        a1, a2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+        d = man.dist(a1, a2)
+        assert d.shape == (z1.shape[0],)
+        (d * go).sum().backward()
+        np.testing.assert_allclose(d.detach().cpu().numpy(), r["dist_" + m], rtol=RTOL)
+        np.testing.assert_allclose(man.vvd(z1, z2).cpu().numpy(), r["vvd"], rtol=RTOL, atol=ATOL)
+        gmax = max(np.abs(r["g1_" + m]).max(), np.abs(r["g2_" + m]).max())
+        assert np.abs(a1.grad.cpu().numpy() - sym(r["g1_" + m])).max() <= grad_tolerance(n) * gmax
+        assert np.abs(a2.grad.cpu().numpy() - sym(r["g2_" + m])).max() <= grad_tolerance(n) * gmax
+        if m == "wsum":
+            np.testing.assert_allclose(man.metric.weights.grad.cpu().numpy(), r["gw_wsum"], rtol=1e-9)
+        with torch.no_grad():
+            d0 = man.dist(z1, z2)
+        assert torch.equal(d0, d.detach())      # forward-only kernel == forward+grad kernel
+    sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n,metric", [("upper", 2, "riem"), ("upper", 4, "fmin"), ("bounded", 3, "fone"),
+                                           ("upper", 6, "finf"), ("bounded", 5, "wsum"), ("upper", 10, "fmin"),
+                                           ("spd", 3, "riem"), ("spd", 4, "riem"), ("spd", 10, "riem")])
+def test_table_path_and_fused_step_match_oracle(sb, kind, n, metric):
+    """fused gather + scatter-add backward, and the one-launch distortion step, against the oracle
+    run the way the reference runs it: gather -> dist -> AverageDistortionLoss -> autograd."""
+    g = torch.Generator().manual_seed(100 + n)
+    rows, b = 37, 200
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g)
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+    src = torch.randint(0, rows, (b,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1)
+    gdist = torch.randint(1, 20, (b,), generator=g).double()
+    scale = 1.7
+    w = torch.linspace(-0.2, 1.1, n).reshape(1, n) if metric == "wsum" else None
+
+    # oracle
+    tab_o = table.clone().requires_grad_(True)
+    w_o = None if w is None else w.clone().requires_grad_(True)
+    d_o = so.dist(kind, tab_o[idx[:, 0]], tab_o[idx[:, 1]], metric, w_o)
+    loss_o = so.distortion_loss(gdist, d_o * scale)
+    loss_o.backward()
+    gt_o = sym(tab_o.grad.numpy())
+    tol = grad_tolerance(n) * np.abs(gt_o).max()
+
+    # CUDA, autograd path through the table
+    man = (sb.SymmetricPositiveDefinite().cuda() if kind == "spd" else make_manifold(sb, kind, n, metric, None if w is None else w.numpy()))
+    tab_c = table.cuda().requires_grad_(True)
+    d_c = man.dist_from_table(tab_c, idx.cuda())
+    loss_c = so.distortion_loss(gdist.cuda(), d_c * scale)
+    loss_c.backward()
+    np.testing.assert_allclose(d_c.detach().cpu().numpy(), d_o.detach().numpy(), rtol=RTOL)
+    np.testing.assert_allclose(loss_c.item(), loss_o.item(), rtol=1e-9)
+    assert np.abs(tab_c.grad.cpu().numpy() - gt_o).max() <= tol
+    if w is not None:
+        np.testing.assert_allclose(man.metric.weights.grad.cpu().numpy(), w_o.grad.numpy(), rtol=1e-8, atol=1e-10)
+
+    # CUDA, fused one-launch step
+    gt = torch.zeros_like(tab_c)
+    gs = torch.zeros(1, dtype=torch.float64, device="cuda")
+    gw = torch.zeros(n, dtype=torch.float64, device="cuda") if w is not None else None
+    dist_out = torch.empty(b, dtype=torch.float64, device="cuda")
+    loss = sb.ops.distortion_step(kind, metric, tab_c.detach(), idx.cuda(), gdist.cuda(), scale, gt,
+                                  wsum_w=None if w is None else w.cuda(), grad_wsum_w=gw, grad_scale=gs,
+                                  dist_out=dist_out)
+    np.testing.assert_allclose(loss.item(), loss_o.item(), rtol=1e-9)
+    np.testing.assert_allclose(dist_out.cpu().numpy(), d_o.detach().numpy(), rtol=RTOL)
+    assert np.abs(gt.cpu().numpy() - gt_o).max() <= tol
+    if w is not None:
+        np.testing.assert_allclose(gw.cpu().numpy(), w_o.grad.numpy().reshape(-1), rtol=1e-8, atol=1e-10)
+    # d loss / d scale = sum sign * 2 r * d / g
+    s_o = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+    so.distortion_loss(gdist, d_o.detach() * s_o).backward()
+    np.testing.assert_allclose(gs.item(), s_o.grad.item(), rtol=1e-9)
+    sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind", ["upper", "bounded"])
+@pytest.mark.parametrize("n", [2, 3, 4, 6])
+def test_reference_metamorphic_properties(sb, kind, n):
+    """tests/test_upper_half.py:109-186 and tests/test_bounded_domain.py:95-127 of the reference."""
+    man = make_manifold(sb, kind, n, "riem")
+    x, y = man.random(10).cuda(), man.random(10).cuda()
+    torch.testing.assert_close(man.dist(x, y), man.dist(y, x), rtol=1e-5, atol=1e-8)
+    dxx = man.dist(x, x)
+    torch.testing.assert_close(dxx, torch.zeros_like(dxx), rtol=0, atol=1e-8)
+    eye = torch.eye(n, dtype=torch.bool, device="cuda").expand(10, 2, n, n)
+    xd, yd = torch.where(eye, x, torch.zeros_like(x)), torch.where(eye, y, torch.zeros_like(y))
+    torch.testing.assert_close(man.dist(xd, yd), man.dist(yd, xd), rtol=1e-5, atol=1e-8)
+    ref = so.dist(kind, xd.cpu(), yd.cpu())
+    torch.testing.assert_close(man.dist(xd, yd).cpu(), ref, rtol=1e-9, atol=1e-12)
+    if kind == "upper":
+        xi = torch.stack((torch.zeros_like(x[:, 0]), x[:, 1]), 1)
+        yi = torch.stack((torch.zeros_like(y[:, 0]), y[:, 1]), 1)
+        torch.testing.assert_close(man.dist(xi, yi), man.dist(yi, xi), rtol=1e-5, atol=1e-8)
+        torch.testing.assert_close(man.dist(xi, yi).cpu(), so.dist(kind, xi.cpu(), yi.cpu()), rtol=1e-9, atol=1e-12)
+    sb.ops.check_status()
+
+
+def test_edge_cases(sb):
+    man = make_manifold(sb, "upper", 3, "riem")
+    # empty batch
+    e = torch.empty(0, 2, 3, 3, dtype=torch.float64, device="cuda")
+    assert man.dist(e, e).shape == (0,)
+    # point outside the manifold -> status bit, raised lazily
+    x = man.random(4).cuda()
+    bad = x.clone()
+    bad[:, 1] = -bad[:, 1]
+    man.dist(bad, x)
+    with pytest.raises(AssertionError, match="outside the manifold"):
+        sb.ops.check_status()
+    sb.ops.check_status()   # reset
+    # out-of-range index -> status bit, pair skipped
+    table = man.random(5).cuda()
+    idx = torch.tensor([[0, 1], [2, 7]], device="cuda")
+    d = man.dist_from_table(table, idx)
+    assert d[1].item() == 0.0
+    with pytest.raises(AssertionError, match="index out of range"):
+        sb.ops.check_status()
+    # wrong dtype / shape / n
+    with pytest.raises(TypeError):
+        man.dist(x.float(), x.float())
+    with pytest.raises(ValueError):
+        man.dist(x[:, 0], x[:, 0])
+    big = torch.zeros(1, 2, 11, 11, dtype=torch.float64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        man.dist(big, big)
+    # repeated rows inside one batch accumulate (atomics)
+    table = man.random(3).cuda().requires_grad_(True)
+    idx = torch.tensor([[0, 1]] * 64, device="cuda")
+    man.dist_from_table(table, idx).sum().backward()
+    one = man.random(3).cuda()
+    t1 = table.detach().clone().requires_grad_(True)
+    man.dist_from_table(t1, idx[:1]).sum().backward()
+    torch.testing.assert_close(table.grad, 64 * t1.grad, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 2), ("upper", 4), ("bounded", 3), ("upper", 10)])
+def test_full_size_properties(sb, kind, n):
+    """Size-independent properties at a BASELINE-sized batch: symmetry d(a,b) = d(b,a), d(a,a) = 0,
+    riem^2 = sum vvd^2, fone = sum vvd, finf = max vvd, ascending vvd, and conservation of the
+    scatter-add (sum of the table gradient == sum of per-pair gradients)."""
+    rows = 1 << 16
+    b = (1 << 20) if n <= 4 else (1 << 17)
+    g = torch.Generator().manual_seed(9)
+    table = so.upper_spread(rows, n, generator=g, scale=0.3)
+    if kind == "bounded":
+        table = so.to_symmetric(so.cayley_transform(table))
+    table = table.cuda()
+    src = torch.randint(0, rows, (b,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    out = {}
+    for m in ("riem", "fone", "finf"):
+        man = make_manifold(sb, kind, n, m)
+        with torch.no_grad():
+            out[m] = man.dist_from_table(table, idx)
+            rev = man.dist_from_table(table, idx.flip(1))
+        torch.testing.assert_close(out[m], rev, rtol=1e-9, atol=1e-12)
+    v = man.vvd(table[idx[:, 0]], table[idx[:, 1]])
+    assert bool((v[:, 1:] >= v[:, :-1]).all())
+    torch.testing.assert_close(out["riem"], v.norm(dim=-1), rtol=1e-12, atol=0)
+    torch.testing.assert_close(out["fone"], v.sum(-1), rtol=1e-12, atol=0)
+    torch.testing.assert_close(out["finf"], v[:, -1], rtol=0, atol=0)
+    same = torch.stack((idx[:, 0], idx[:, 0]), 1)
+    with torch.no_grad():
+        dxx = man.dist_from_table(table, same)
+    assert dxx.abs().max().item() < 1e-7
+    t = table.clone().requires_grad_(True)
+    man = make_manifold(sb, kind, n, "riem")
+    man.dist_from_table(t, idx).sum().backward()
+    z1 = table[idx[:, 0]].requires_grad_(True)
+    z2 = table[idx[:, 1]].requires_grad_(True)
+    man.dist(z1, z2).sum().backward()
+    total = z1.grad.sum(0) + z2.grad.sum(0)
+    torch.testing.assert_close(t.grad.sum(0), total, rtol=1e-8, atol=1e-8)
+    sb.ops.check_status()
