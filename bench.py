@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the Siegel pair-distance hot path (BASELINE.json metric: pairs/s forward+backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4] [--kind upper]
+
+Workload (config.workload): BASELINE.json configs[4] 'distance microbench' - a table of 2^20 random
+points, B index pairs per GPU per step, manifold `--kind` with n x n matrices, metric riem, forward
++ backward through the distortion loss (sympa/losses.py:16-19).  One step = gather -> dist ->
+loss -> backward -> scatter-add into the dense table gradient (+ NCCL all-reduce of that gradient
+when N > 1).  `value` is measured with everything resident in HBM; `e2e` runs the same step through
+the public manifold API with the step's inputs (index pairs, graph distances) copied from pinned
+host memory and the loss read back, inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def algorithmic_bytes_per_pair(kind, n):
+    """read two rows, accumulate two gradient rows, two int64 indices, vvd out, dist
+    out, upstream gradient in."""
+    if kind == "spd":
+        return 32 * n * n + 8 * n + 32
+    return 64 * n * n + 8 * n + 32
+
+
+def lean_flops_per_pair(n):
+    return 100 * n ** 3   # SURVEY.md 8(d) yardstick F_lean
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_table(kind, n, rows, device, seed):
+    """'spread' regime of SURVEY.md 8(d), scale 0.3: X = sym(0.3 N(0,1)), Y = C C^T + 0.5 I."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    c = 0.3 * torch.randn(rows, n, n, dtype=torch.float64, device=device, generator=g)
+    y = c @ c.transpose(-1, -2) + 0.5 * torch.eye(n, dtype=torch.float64, device=device)
+    y = 0.5 * (y + y.transpose(-1, -2))
+    if kind == "spd":
+        return y.contiguous()
+    x = 0.3 * torch.randn(rows, n, n, dtype=torch.float64, device=device, generator=g)
+    x = 0.5 * (x + x.transpose(-1, -2))
+    z = torch.stack((x, y), 1).contiguous()
+    if kind == "bounded":
+        from sympa_b200.manifolds import csym
+        out = torch.empty_like(z)
+        for s in range(0, rows, 1 << 16):
+            out[s:s + (1 << 16)] = csym.to_symmetric(csym.cayley_transform(z[s:s + (1 << 16)]))
+        z = out
+    return z
+
+
+def make_pairs(rows, b, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    src = torch.randint(0, rows, (b,), device=device, generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), device=device, generator=g)) % rows   # src != dst
+    gd = torch.randint(1, 21, (b,), device=device, generator=g).double()
+    return torch.stack((src, dst), 1).contiguous(), gd
+
+
+def distortion_loss(graph_dist, manifold_dist):   # sympa/losses.py:16-19, torch ops on (b,) vectors
+    return torch.abs(torch.pow(manifold_dist / graph_dist, 2) - 1).sum()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sympa_b200 import BoundedDomainManifold, MetricType, SymmetricPositiveDefinite, UpperHalfManifold, ops
+    from sympa_b200 import distributed as sd
+
+    rank, world, local = sd.init_process_group()
+    assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    dev = torch.device("cuda", local)
+    kind, n = args.kind, args.n
+    rows = args.rows
+    b = args.pairs if args.pairs else ((1 << 22) if n <= 4 else (1 << 19 if n <= 6 else 1 << 16))
+    if kind == "spd":
+        man = SymmetricPositiveDefinite().to(dev)
+    else:
+        man = {"upper": UpperHalfManifold, "bounded": BoundedDomainManifold}[kind](
+            dims=n, metric=MetricType.from_str(args.metric)).to(dev)
+    table = make_table(kind, n, rows, dev, seed=1).requires_grad_(True)     # replicated on every rank
+    idx, gd = make_pairs(rows, b, dev, seed=100 + rank)                       # each rank its own shard
+    scale = 1.0
+
+    def step_resident():
+        table.grad = None
+        d = man.dist_from_table(table, idx)
+        loss = distortion_loss(gd, d * scale)
+        loss.backward()
+        if world > 1:
+            sd.allreduce_gradients([table.grad], average=True)
+        return loss
+
+    # host-resident inputs for the e2e leg
+    idx_h = idx.cpu().pin_memory()
+    gd_h = gd.cpu().pin_memory()
+    idx_d = torch.empty_like(idx)
+    gd_d = torch.empty_like(gd)
+    loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        idx_d.copy_(idx_h, non_blocking=True)
+        gd_d.copy_(gd_h, non_blocking=True)
+        table.grad = None
+        d = man.dist_from_table(table, idx_d)
+        loss = distortion_loss(gd_d, d * scale)
+        loss.backward()
+        if world > 1:
+            sd.allreduce_gradients([table.grad], average=True)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, fwd_events=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ops.check_status(dev)
+
+    # dominant kernel (forward + unit gradients) timed alone inside the same loop shape
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = world * b * args.steps / (ms_total * 1e-3)
+
+    # per-kernel durations with CUDA events on the launching (current) stream
+    fwd_ms, bwd_ms = [], []
+    for _ in range(min(args.steps, 10)):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.no_grad():
+            ev[0].record()
+            dd, vv, saved = ops.forward_raw(kind, args.metric if kind != "spd" else "riem", table=table.detach(), idx=idx,
+                                            wsum_w=None, want_grad=True)
+            ev[1].record()
+        g = torch.ones_like(dd)
+        gt = torch.zeros_like(table)
+        from sympa_b200 import _lib
+        lib = _lib.load()
+        ev[2].record()
+        _lib.check(lib.sympa_dist_backward(_lib.KIND[kind], n, _lib.METRIC["riem"], b, g.data_ptr(), saved.data_ptr(),
+                                           None, None, gt.data_ptr(), rows, idx.data_ptr(), None, None, None,
+                                           torch.cuda.current_stream().cuda_stream))
+        ev[3].record()
+        torch.cuda.synchronize()
+        fwd_ms.append(ev[0].elapsed_time(ev[1]))
+        bwd_ms.append(ev[2].elapsed_time(ev[3]))
+        del saved, dd, vv, gt
+    fwd = statistics.mean(fwd_ms)
+    bwd = statistics.mean(bwd_ms)
+
+    # fused single-launch step (extension: on-device loss), for comparison
+    gt = torch.zeros_like(table)
+    loss_out = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step_fused():
+        gt.zero_()
+        loss_out.zero_()
+        ops.distortion_step(kind, args.metric if kind != "spd" else "riem", table.detach(), idx, gd, scale, gt,
+                            loss_out=loss_out)
+    for _ in range(3):
+        step_fused()
+    ms_fused = timed(step_fused, args.steps) / args.steps
+    del gt
+
+    # e2e
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e_value = world * b * args.steps / (ms_e2e * 1e-3)
+    ops.check_status(dev)
+
+    peaks, peak_kind = load_peaks()
+    abytes = algorithmic_bytes_per_pair(kind, n) * b
+    achieved = abytes / (fwd * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"pair_kernel<{n},{kind},fwd+unit-grad>", "achieved": round(achieved, 2),
+        "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+        "traffic": None, "kernel_ms": round(fwd, 4), "scatter_kernel_ms": round(bwd, 4),
+        "fp64_lean_tflops": round(lean_flops_per_pair(n) * b / (fwd * 1e-3) / 1e12, 3),
+        "fp64_nominal_peak_tflops": 37.2,
+        "note": "executes on the FP64 pipe (Jacobi sweeps); HBM fraction uses algorithmic bytes 64n^2+8n+32 per pair",
+    }
+    out = {
+        "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"distance microbench: {kind} n={n} metric={args.metric}, table 2^{rows.bit_length() - 1} rows, "
+                               f"{b} pairs/GPU/step, fwd+bwd through AverageDistortionLoss",
+                   "pairs_per_gpu_per_step": b, "rows": rows, "n": n, "kind": kind, "metric": args.metric,
+                   "l2": "table + saved unit gradients + indices exceed L2 every step (no explicit flush needed)",
+                   "parallelism": f"dp{world} pairs sharded, table replicated, one NCCL all-reduce of the table gradient"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(idx_h.numel() * 8 + gd_h.numel() * 8),
+                "d2h_bytes_per_step": 8},
+        "gpu_launches": 2 * args.steps,
+        "fused_step": {"pairs_per_s": world * b / (ms_fused * 1e-3), "ms_per_step": ms_fused, "launches_per_step": 1},
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(kind, n, args.metric, budget_s=args.cpu_budget)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
+    """The oracle port (the reference's own torch op sequence, oracle/siegel_oracle.py) timed on the
+    host cores: gather -> dist -> distortion loss -> autograd backward, float64."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import siegel_oracle as so
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rows = 1 << 14
+    table = make_table(kind, n, rows, torch.device("cpu"), seed=1).requires_grad_(True)
+    b = 1 << 14
+    idx, gd = make_pairs(rows, b, torch.device("cpu"), seed=100)
+
+    def step():
+        table.grad = None
+        d = so.dist(kind, table[idx[:, 0]], table[idx[:, 1]], metric if kind != "spd" else "riem")
+        distortion_loss(gd, d).backward()
+
+    step()
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        step()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or reps >= 50:
+            break
+    return {"value": b * reps / el, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x {b} pairs of the same workload ({kind} n={n}), torch CPU float64, {el:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, n = args.kind, args.n
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import siegel_oracle as so
+    torch.set_num_threads(threads)
+    rows = 1 << 14
+    b = 1 << 13
+    table = make_table(kind, n, rows, torch.device("cpu"), seed=1).requires_grad_(True)
+    idx, gd = make_pairs(rows, b, torch.device("cpu"), seed=100)
+
+    def step():
+        table.grad = None
+        d = so.dist(kind, table[idx[:, 0]], table[idx[:, 1]], args.metric if kind != "spd" else "riem")
+        distortion_loss(gd, d).backward()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = b * args.steps / el
+    cfg_b = args.pairs if args.pairs else ((1 << 22) if n <= 4 else (1 << 19 if n <= 6 else 1 << 16))
+    out = {
+        "impl": "reference", "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"distance microbench: {kind} n={n} metric={args.metric}, table 2^{args.rows.bit_length() - 1} rows, "
+                               f"{cfg_b} pairs/GPU/step, fwd+bwd through AverageDistortionLoss",
+                   "n": n, "kind": kind, "metric": args.metric},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = {b} pairs of the workload (bounded sample), table 2^14 rows, torch CPU float64"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kind", default="upper", choices=["upper", "bounded", "spd"])
+    ap.add_argument("--n", type=int, default=4)
+    ap.add_argument("--metric", default="riem")
+    ap.add_argument("--rows", type=int, default=1 << 20)
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default by n)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,10 @@ def forward_raw(kind, metric, z1=None, z2=None, table=None, idx=None, wsum_w=Non
         dist = torch.empty(b, dtype=torch.float64, device=dev)
         vvd = torch.empty(b, n, dtype=torch.float64, device=dev) if want_vvd else None
         saved = None
+        if b == 0:   # nothing to launch (an empty tensor has a null data pointer)
+            if want_grad:
+                saved = torch.empty(0, dtype=torch.float64, device=dev)
+            return dist, vvd, saved
         if want_grad:
             nbytes = lib.sympa_workspace_bytes(_lib.KIND[kind], n, b)
             saved = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
@@ -124,6 +128,9 @@ class _DistFn(torch.autograd.Function):
         grad_dist = _require(grad_dist, "grad_dist")
         b, n = vvd.shape
         dev = vvd.device
+        if b == 0:
+            z = torch.zeros(ctx.shape, dtype=torch.float64, device=dev)
+            return z, z.clone(), (None if wsum_w is None else torch.zeros_like(wsum_w)), None, None
         with torch.cuda.device(dev):
             g1 = torch.empty(ctx.shape, dtype=torch.float64, device=dev)
             g2 = torch.empty(ctx.shape, dtype=torch.float64, device=dev)
@@ -161,6 +168,9 @@ class _TableDistFn(torch.autograd.Function):
         grad_dist = _require(grad_dist, "grad_dist")
         b, n = vvd.shape
         dev = vvd.device
+        if b == 0:
+            return (torch.zeros(ctx.tshape, dtype=torch.float64, device=dev), None,
+                    (None if wsum_w is None else torch.zeros_like(wsum_w)), None, None)
         with torch.cuda.device(dev):
             gt = torch.zeros(ctx.tshape, dtype=torch.float64, device=dev)
             gw = None

@@ -74,7 +74,7 @@ def test_table_path_and_fused_step_match_oracle(sb, kind, n, metric):
     idx = torch.stack((src, dst), 1)
     gdist = torch.randint(1, 20, (b,), generator=g).double()
     scale = 1.7
-    w = torch.linspace(-0.2, 1.1, n).reshape(1, n) if metric == "wsum" else None
+    w = torch.linspace(-0.2, 1.1, n, dtype=torch.float64).reshape(1, n) if metric == "wsum" else None
 
     # oracle
     tab_o = table.clone().requires_grad_(True)
