@@ -246,12 +246,26 @@ static int launch_one(const PairArgs& a, cudaStream_t s) {
   return check_launch();
 }
 
+template <int N, int KIND, int MODE>
+static int launch_coop(const PairArgs& a, cudaStream_t s);  // coop_kernels.cuh
+
+// kernel selection: one pair per thread in registers for n <= SY_REG_MAX_N; warp-cooperative shared
+// memory kernel for the larger upper-half sizes; rolled per-thread fallback otherwise.
+template <int N, int KIND, int MODE>
+static int launch_any(const PairArgs& a, cudaStream_t s) {
+  if constexpr (KIND == kUpper && (N > SY_REG_MAX_N)) {
+    return launch_coop<N, KIND, MODE>(a, s);
+  } else {
+    return launch_one<N, KIND, MODE>(a, s);
+  }
+}
+
 template <int N, int KIND>
 static int launch_mode(int mode, const PairArgs& a, cudaStream_t s) {
   switch (mode) {
-    case kModeFwd: return launch_one<N, KIND, kModeFwd>(a, s);
-    case kModeFwdSave: return launch_one<N, KIND, kModeFwdSave>(a, s);
-    case kModeStep: return launch_one<N, KIND, kModeStep>(a, s);
+    case kModeFwd: return launch_any<N, KIND, kModeFwd>(a, s);
+    case kModeFwdSave: return launch_any<N, KIND, kModeFwdSave>(a, s);
+    case kModeStep: return launch_any<N, KIND, kModeStep>(a, s);
   }
   return 1;
 }

@@ -4,6 +4,7 @@
 #endif
 #define SYMPA_PAIR_KERNELS_IMPL
 #include "pair_kernels.cuh"
+#include "coop_kernels.cuh"
 
 namespace sympa {
 template int launch_pairs<SYMPA_TU_N>(int, int, const PairArgs&, cudaStream_t);

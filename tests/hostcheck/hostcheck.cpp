@@ -2,8 +2,11 @@
 // per-pair templates the CUDA kernels instantiate can be checked against the golden vectors on a
 // machine without a GPU (tests/test_hostcheck.py).  Never loaded by the product package.
 //   variant 0 = namespace sympa::reg (unrolled, what the kernels use for n <= 4)
-//   variant 1 = namespace sympa::loc (rolled loops, what the kernels use for n > 4)
+//   variant 1 = namespace sympa::loc (rolled loops, per-thread fallback)
+//   variant 2 = namespace sympa::coop (warp-cooperative shared-memory kernels, lanes emulated sequentially)
 #include "../../sympa_b200/csrc/pair_math.cuh"
+#include "../../sympa_b200/csrc/coop_math.cuh"
+#include <vector>
 
 using namespace sympa;
 
@@ -58,6 +61,38 @@ using namespace sympa;
 HC_RUN(reg)
 HC_RUN(loc)
 
+template <int N>
+static void run_coop(int kind, int metric, int64_t b, const double* z1, const double* z2, const double* w, int grad,
+                     double* dist, double* vvd, double* g1, double* g2, unsigned* status) {
+  typedef coop::Layout<N> L;
+  const int per = 2 * N * N;
+  std::vector<double> sm(L::kDoubles);
+  coop::HostExec ex{L::G};
+  for (int64_t p = 0; p < b; ++p) {
+    for (auto& x : sm) x = -7.0e300;  // poison: any read of an unwritten slot shows up
+    if (grad)
+      coop::upper_pair<N, true>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+    else
+      coop::upper_pair<N, false>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+    dist[p] = sm[L::DIST];
+    for (int k = 0; k < N; ++k) vvd[p * N + k] = sm[L::VS + k];
+    *status |= (unsigned)sm[L::FLAG];
+    if (grad) {
+      const double* gx2 = &sm[L::Q];
+      const double* gy2 = &sm[L::T2];
+      const double* gy1 = &sm[L::P];
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+          const int e = i * N + j, et = j * N + i;
+          g2[p * per + e] = 0.5 * (gx2[e] + gx2[et]);
+          g2[p * per + N * N + e] = 0.5 * (gy2[e] + gy2[et]);
+          g1[p * per + e] = -0.5 * (gx2[e] + gx2[et]);
+          g1[p * per + N * N + e] = 0.5 * (gy1[e] + gy1[et]);
+        }
+    }
+  }
+}
+
 extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b, const double* z1, const double* z2,
                              const double* w, int grad, double* dist, double* vvd, double* g1, double* g2,
                              unsigned* status) {
@@ -65,6 +100,15 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
     switch (n) {
 #define CASE(K) case K: run_reg<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
       CASE(1) CASE(2) CASE(3) CASE(4)
+#undef CASE
+    }
+    return 1;
+  }
+  if (variant == 2) {
+    if (kind != kUpper) return 1;
+    switch (n) {
+#define CASE(K) case K: run_coop<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
+      CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     }
     return 1;
