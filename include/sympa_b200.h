@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SYMPA_ABI_VERSION 1
+#define SYMPA_ABI_VERSION 2
 
 /* manifold kinds: sympa/embeddings.py:144-149 ("upper", "bounded") and :142 ("spd") */
 enum { SYMPA_KIND_UPPER = 0, SYMPA_KIND_BOUNDED = 1, SYMPA_KIND_SPD = 2 };
@@ -58,6 +58,13 @@ const char* sympa_last_cuda_error(void);
  * the per-pair unit gradients d dist / d z1, d dist / d z2, i.e. 2 * num_pairs * point_doubles * 8. */
 int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs);
 
+/* bytes of optional `scratch` (device memory, contents irrelevant, may be reused by the next call on
+ * the same stream) that lets sympa_dist_forward / sympa_distortion_step run the larger matrix sizes
+ * (upper half space, n > 4) as three kernels with the per-pair state parked in scratch instead of
+ * shared memory (~2x faster there).  0 when the configuration does not use scratch.  Passing
+ * scratch == NULL (or fewer bytes) is always valid: the single-kernel path is used. */
+int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
+
 /* Forward of manifold.dist (siegel_manifold.py:41-72, bounded_domain.py:27-39, geoopt spd dist).
  * Operands come either materialised (z1, z2: (num_pairs, point)) or as a fused gather
  * (table + idx; replaces Embeddings.forward, sympa/embeddings.py:29-34).  Exactly one of the two
@@ -69,6 +76,7 @@ int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs,
                        const double* table, int64_t num_rows, const int64_t* idx,
                        const double* wsum_w,
                        double* dist_out, double* vvd_out, double* saved_state,
+                       double* scratch, int64_t scratch_bytes,
                        unsigned int* status, void* stream);
 
 /* Backward: replaces autograd through the ~250 torch ops of dist plus the gather backward.
@@ -92,7 +100,8 @@ int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs,
                           const double* table, int64_t num_rows, const int64_t* idx,
                           const double* graph_dist, double scale, const double* wsum_w,
                           double* grad_table, double* grad_wsum_w, double* grad_scale, double* loss_out,
-                          double* dist_out, unsigned int* status, void* stream);
+                          double* dist_out, double* scratch, int64_t scratch_bytes,
+                          unsigned int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ EXPORTS = (
     "sympa_error_string",
     "sympa_last_cuda_error",
     "sympa_workspace_bytes",
+    "sympa_scratch_bytes",
     "sympa_dist_forward",
     "sympa_dist_backward",
     "sympa_distortion_step",
@@ -51,12 +52,14 @@ def load():
     lib.sympa_last_cuda_error.restype = ctypes.c_char_p
     lib.sympa_workspace_bytes.restype = L
     lib.sympa_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_scratch_bytes.restype = L
+    lib.sympa_scratch_bytes.argtypes = [I, I, L]
     lib.sympa_dist_forward.restype = I
-    lib.sympa_dist_forward.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, P, P]
+    lib.sympa_dist_forward.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, P, L, P, P]
     lib.sympa_dist_backward.restype = I
     lib.sympa_dist_backward.argtypes = [I, I, I, L, P, P, P, P, P, L, P, P, P, P, P]
     lib.sympa_distortion_step.restype = I
-    lib.sympa_distortion_step.argtypes = [I, I, I, L, P, L, P, P, D, P, P, P, P, P, P, P, P]
+    lib.sympa_distortion_step.argtypes = [I, I, I, L, P, L, P, P, D, P, P, P, P, P, P, P, L, P, P]
     _lib = lib
     return lib
 

@@ -78,19 +78,20 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
         for (int k = g; k < N; k += G) a.vvd_out[p * N + k] = sm[L::VS + k];
       }
       if (GRAD) {
-        const double* gx2 = sm + L::Q;
-        const double* gy2 = sm + L::T2;
-        const double* gy1 = sm + L::P;
+        const double* gx2 = sm + L::GX2;
+        const double* gy2 = sm + L::GY2;
+        const double* gy1 = sm + L::GY1;
+        constexpr int LD = L::LD;
         if (MODE == kModeFwdSave) {
           double* o1 = a.gz1 + p * PER;
           double* o2 = a.gz2 + p * PER;
           for (int e = g; e < NN; e += G) {
-            const int et = (e % N) * N + e / N;
-            const double x2 = 0.5 * (gx2[e] + gx2[et]);
+            const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+            const double x2 = 0.5 * (gx2[s] + gx2[t]);
             o2[e] = x2;
             o1[e] = -x2;
-            o2[NN + e] = 0.5 * (gy2[e] + gy2[et]);
-            o1[NN + e] = 0.5 * (gy1[e] + gy1[et]);
+            o2[NN + e] = 0.5 * (gy2[s] + gy2[t]);
+            o1[NN + e] = 0.5 * (gy1[s] + gy1[t]);
           }
         } else {  // fused distortion step
           const double gd = __ldg(a.graph_dist + p);
@@ -110,12 +111,12 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
           double* o1 = a.grad_table + i1 * PER;
           double* o2 = a.grad_table + i2 * PER;
           for (int e = g; e < NN; e += G) {
-            const int et = (e % N) * N + e / N;
-            const double x2 = dl_dd * 0.5 * (gx2[e] + gx2[et]);
+            const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+            const double x2 = dl_dd * 0.5 * (gx2[s] + gx2[t]);
             atomicAdd(o2 + e, x2);
             atomicAdd(o1 + e, -x2);
-            atomicAdd(o2 + NN + e, dl_dd * 0.5 * (gy2[e] + gy2[et]));
-            atomicAdd(o1 + NN + e, dl_dd * 0.5 * (gy1[e] + gy1[et]));
+            atomicAdd(o2 + NN + e, dl_dd * 0.5 * (gy2[s] + gy2[t]));
+            atomicAdd(o1 + NN + e, dl_dd * 0.5 * (gy1[s] + gy1[t]));
           }
         }
       }
@@ -132,6 +133,237 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
   }
   st = __reduce_or_sync(0xffffffffu, st);
   if (st != 0 && lane == 0 && a.status != nullptr) atomicOr(a.status, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split path: the same pipeline as three kernels with the per-pair state parked in global scratch
+// (L2-resident for the chunk sizes used).  The Jacobi kernel then only needs the two halves of G in
+// shared memory, so four to five times more pairs are resident per SM while the latency-bound
+// rotation chains run - which is where ~70 % of the FP64 work is.
+struct ChunkArgs {
+  double* scratch;
+  int64_t cap;    // scratch capacity in pairs
+  int64_t base;   // first pair of this chunk
+  int64_t count;  // pairs in this chunk (<= cap)
+};
+
+template <int N>
+__device__ __forceinline__ bool locate_pair(const PairArgs& a, int64_t p, const double** p1, const double** p2,
+                                            int64_t* i1, int64_t* i2) {
+  constexpr int PER = 2 * N * N;
+  if (a.idx != nullptr) {
+    *i1 = __ldg(a.idx + 2 * p);
+    *i2 = __ldg(a.idx + 2 * p + 1);
+    if (*i1 < 0 || *i1 >= a.num_rows || *i2 < 0 || *i2 >= a.num_rows) return false;
+    *p1 = a.table + *i1 * PER;
+    *p2 = a.table + *i2 * PER;
+  } else {
+    *p1 = a.z1 + p * PER;
+    *p2 = a.z2 + p * PER;
+  }
+  return true;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) coop_prologue_kernel(const PairArgs a, const ChunkArgs c) {
+  typedef coop::Layout<N> L;
+  constexpr int G = CoopCfg<N>::G;
+  constexpr int PW = CoopCfg<N>::PW;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  const int slot = lane / G;
+  const int g = lane - slot * G;
+  double* sm = smem + (slot < PW ? slot : 0) * L::kDoubles;
+  unsigned st = 0;
+  const int64_t stride = (int64_t)gridDim.x * PW;
+  for (int64_t base = (int64_t)blockIdx.x * PW; base < c.count; base += stride) {
+    const int64_t q = base + slot;
+    bool active = slot < PW && q < c.count;
+    const double* p1 = nullptr;
+    const double* p2 = nullptr;
+    int64_t i1, i2;
+    if (active && !locate_pair<N>(a, c.base + q, &p1, &p2, &i1, &i2)) {
+      st |= kStatusBadIndex;
+      if (g == 0 && a.dist_out) a.dist_out[c.base + q] = 0.0;
+      active = false;
+    }
+    WarpExec ex{g, active};
+    coop::split_prologue<N>(ex, sm, p1, p2, c.scratch, c.cap, q);
+    if (active && g == 0 && sm[L::FLAG] != 0.0) st |= kStatusNotPD;
+    __syncwarp();
+  }
+  st = __reduce_or_sync(0xffffffffu, st);
+  if (st != 0 && lane == 0 && a.status != nullptr) atomicOr(a.status, st);
+}
+
+template <int N, bool GRAD>
+__global__ void __launch_bounds__(32) coop_spectrum_kernel(const PairArgs a, const ChunkArgs c) {
+  typedef coop::LayoutJ<N> L;
+  constexpr int G = CoopCfg<N>::G;
+  constexpr int PW = CoopCfg<N>::PW;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  const int slot = lane / G;
+  const int g = lane - slot * G;
+  double* sm = smem + (slot < PW ? slot : 0) * L::kDoubles;
+  unsigned st = 0;
+  const int64_t stride = (int64_t)gridDim.x * PW;
+  for (int64_t base = (int64_t)blockIdx.x * PW; base < c.count; base += stride) {
+    const int64_t q = base + slot;
+    const int64_t p = c.base + q;
+    bool active = slot < PW && q < c.count;
+    if (active && a.idx != nullptr) {
+      const int64_t i1 = __ldg(a.idx + 2 * p), i2 = __ldg(a.idx + 2 * p + 1);
+      if (i1 < 0 || i1 >= a.num_rows || i2 < 0 || i2 >= a.num_rows) active = false;
+    }
+    WarpExec ex{g, active};
+    coop::split_spectrum<N, GRAD>(ex, sm, a.metric, a.wsum_w, c.scratch, c.cap, q);
+    if (active) {
+      if (g == 0) {
+        st |= (unsigned)sm[L::FLAG];
+        if (a.dist_out) a.dist_out[p] = sm[L::DIST];
+      }
+      if (a.vvd_out) {
+        for (int k = g; k < N; k += G) a.vvd_out[p * N + k] = sm[L::VS + k];
+      }
+    }
+    __syncwarp();
+  }
+  st = __reduce_or_sync(0xffffffffu, st);
+  if (st != 0 && lane == 0 && a.status != nullptr) atomicOr(a.status, st);
+}
+
+// writes the unit gradients (MODE fwd+save) or the scaled scatter-add (MODE step) from the results
+// upper_backward left in shared memory
+template <int N, int MODE>
+__device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* sm, int g, int64_t p, int64_t i1,
+                                               int64_t i2, double dist, double* loss_acc, double* gscale_acc) {
+  typedef coop::Layout<N> L;
+  constexpr int G = L::G;
+  constexpr int NN = N * N;
+  constexpr int PER = 2 * NN;
+  constexpr int LD = L::LD;
+  const double* gx2 = sm + L::GX2;
+  const double* gy2 = sm + L::GY2;
+  const double* gy1 = sm + L::GY1;
+  if (MODE == kModeFwdSave) {
+    double* o1 = a.gz1 + p * PER;
+    double* o2 = a.gz2 + p * PER;
+    for (int e = g; e < NN; e += G) {
+      const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+      const double x2 = 0.5 * (gx2[s] + gx2[t]);
+      o2[e] = x2;
+      o1[e] = -x2;
+      o2[NN + e] = 0.5 * (gy2[s] + gy2[t]);
+      o1[NN + e] = 0.5 * (gy1[s] + gy1[t]);
+    }
+  } else {  // fused distortion step: L_p = |(s d / g)^2 - 1|  (losses.py:16-19, model.py:30)
+    const double gd = __ldg(a.graph_dist + p);
+    const double r = a.scale * dist / gd;
+    const double er = r * r - 1.0;
+    const double sg = er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0);
+    const double dl_dr = sg * 2.0 * r;
+    const double dl_dd = dl_dr * a.scale / gd;
+    if (g == 0) {
+      *loss_acc += fabs(er);
+      *gscale_acc += dl_dr * dist / gd;
+    }
+    double* o1 = a.grad_table + i1 * PER;
+    double* o2 = a.grad_table + i2 * PER;
+    for (int e = g; e < NN; e += G) {
+      const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+      const double x2 = dl_dd * 0.5 * (gx2[s] + gx2[t]);
+      atomicAdd(o2 + e, x2);
+      atomicAdd(o1 + e, -x2);
+      atomicAdd(o2 + NN + e, dl_dd * 0.5 * (gy2[s] + gy2[t]));
+      atomicAdd(o1 + NN + e, dl_dd * 0.5 * (gy1[s] + gy1[t]));
+    }
+  }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(32) coop_backward_kernel(const PairArgs a, const ChunkArgs c) {
+  typedef coop::Layout<N> L;
+  constexpr int G = CoopCfg<N>::G;
+  constexpr int PW = CoopCfg<N>::PW;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  const int slot = lane / G;
+  const int g = lane - slot * G;
+  double* sm = smem + (slot < PW ? slot : 0) * L::kDoubles;
+  double loss_acc = 0.0, gscale_acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * PW;
+  for (int64_t base = (int64_t)blockIdx.x * PW; base < c.count; base += stride) {
+    const int64_t q = base + slot;
+    const int64_t p = c.base + q;
+    bool active = slot < PW && q < c.count;
+    const double* p1 = nullptr;
+    const double* p2 = nullptr;
+    int64_t i1 = 0, i2 = 0;
+    if (active && !locate_pair<N>(a, p, &p1, &p2, &i1, &i2)) active = false;
+    WarpExec ex{g, active};
+    coop::split_backward<N>(ex, sm, p1, p2, c.scratch, c.cap, q);
+    if (active) {
+      const double dist = (MODE == kModeStep) ? a.dist_out[p] : 0.0;
+      if (MODE == kModeStep && a.grad_wsum_w != nullptr && a.metric == kWsum) {
+        const double gd = __ldg(a.graph_dist + p);
+        const double r = a.scale * dist / gd;
+        const double er = r * r - 1.0;
+        const double dl_dd = (er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0)) * 2.0 * r * a.scale / gd;
+        for (int k = g; k < N; k += G)
+          if (a.wsum_w[k] > 0.0) atomicAdd(a.grad_wsum_w + k, dl_dd * a.vvd_out[p * N + k]);
+      }
+      emit_gradients<N, MODE>(a, sm, g, p, i1, i2, dist, &loss_acc, &gscale_acc);
+    }
+    __syncwarp();
+  }
+  if (MODE == kModeStep) {
+    loss_acc = warp_sum(loss_acc);
+    gscale_acc = warp_sum(gscale_acc);
+    if (lane == 0) {
+      if (a.loss_out) atomicAdd(a.loss_out, loss_acc);
+      if (a.grad_scale) atomicAdd(a.grad_scale, gscale_acc);
+    }
+  }
+}
+
+template <int N>
+struct SplitCfg {
+  static constexpr int PW = CoopCfg<N>::PW;
+  static constexpr int kSmemFull = CoopCfg<N>::kSmemBytes;
+  static constexpr int kSmemJ = PW * coop::LayoutJ<N>::kDoubles * (int)sizeof(double);
+};
+
+// MODE fwd: prologue + spectrum; fwd+save / step: + backward.  Step needs dist_out and (for wsum)
+// vvd_out as per-pair temporaries: the ABI layer provides them inside the scratch allocation.
+template <int N, int MODE>
+static int launch_split(const PairArgs& a, double* scratch, int64_t cap, cudaStream_t s) {
+  constexpr int PW = SplitCfg<N>::PW;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(coop_prologue_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<N>::kSmemFull);
+    cudaFuncSetAttribute(coop_backward_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SplitCfg<N>::kSmemFull);
+    configured = true;
+  }
+  for (int64_t base = 0; base < a.num_pairs; base += cap) {
+    ChunkArgs c;
+    c.scratch = scratch;
+    c.cap = cap;
+    c.base = base;
+    c.count = (a.num_pairs - base) < cap ? (a.num_pairs - base) : cap;
+    const int64_t groups = (c.count + PW - 1) / PW;
+    const int grid = grid_for(groups, 1, 32 * 8);
+    coop_prologue_kernel<N><<<grid, 32, SplitCfg<N>::kSmemFull, s>>>(a, c);
+    if (MODE == kModeFwd)
+      coop_spectrum_kernel<N, false><<<grid, 32, SplitCfg<N>::kSmemJ, s>>>(a, c);
+    else
+      coop_spectrum_kernel<N, true><<<grid, 32, SplitCfg<N>::kSmemJ, s>>>(a, c);
+    if (MODE != kModeFwd) coop_backward_kernel<N, MODE><<<grid, 32, SplitCfg<N>::kSmemFull, s>>>(a, c);
+    const int rc = check_launch();
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 template <int N, int KIND, int MODE>

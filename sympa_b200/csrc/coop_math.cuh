@@ -23,17 +23,36 @@
 namespace sympa {
 namespace coop {
 
-template <int N>
-struct Layout {
+template <int N, int NBUF>
+struct LayoutT {
   static constexpr int NN = N * N;
+  static constexpr int LD = (N % 2 == 0) ? N + 1 : N;  // odd leading dimension: no systematic bank conflicts
+  static constexpr int BUF = N * LD;                    // one n x n buffer
   static constexpr int NP = (N % 2 == 0) ? N : N + 1;  // padded column count for the tournament
   static constexpr int G = NP / 2;                      // lanes per pair
-  // buffer offsets (doubles) inside one pair's region
-  static constexpr int LI = 0, P = NN, Q = 2 * NN, GR = 3 * NN, GI = 4 * NN, T0 = 5 * NN, T1 = 6 * NN, T2 = 7 * NN;
-  static constexpr int SIG = 8 * NN, COEF = SIG + N, VS = COEF + N, RD = VS + N, WORST = RD + N;  // WORST: 2*G
+  // small per-pair state after the NBUF matrix buffers
+  static constexpr int SIG = NBUF * BUF, COEF = SIG + N, VS = COEF + N, RD = VS + N, VK = RD + N, DV = VK + N, RK = DV + N;
+  static constexpr int WORST = RK + N;  // 2 * G convergence flags (double-buffered by sweep parity)
   static constexpr int DIST = WORST + 2 * G, FLAG = DIST + 1;
   static constexpr int kRaw = FLAG + 1;
-  static constexpr int kDoubles = (kRaw % 2 == 0) ? kRaw + 1 : kRaw;  // odd stride: spreads banks across pair slots
+  static constexpr int kDoubles = (kRaw % 2 == 0) ? kRaw + 1 : kRaw;  // odd stride between pair slots
+};
+
+// full pipeline: LI + six general buffers A0..A5
+template <int N>
+struct Layout : LayoutT<N, 7> {
+  typedef LayoutT<N, 7> B;
+  static constexpr int LI = 0, A0 = B::BUF, A1 = 2 * B::BUF, A2 = 3 * B::BUF, A3 = 4 * B::BUF, A4 = 5 * B::BUF,
+                       A5 = 6 * B::BUF;
+  // where the prologue leaves P and Q, where the Jacobi works, where upper_pair leaves its results
+  static constexpr int PBUF = A0, QBUF = A4, GR = A1, GI = A2;
+  static constexpr int GX2 = A4, GY2 = A3, GY1 = A0;
+};
+
+// Jacobi-only kernel (split path): just the two halves of G
+template <int N>
+struct LayoutJ : LayoutT<N, 2> {
+  static constexpr int GR = 0, GI = LayoutT<N, 2>::BUF;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -58,21 +77,23 @@ struct HostExec {
 };
 
 // ---------------------------------------------------------------------------------------------
+// All shared-memory matrices are n x n with leading dimension LD = Layout<N>::LD.
 // dense helper: accumulate the two owned columns j0 = g, j1 = g + G (j1 may be >= N: ignored)
-//   acc0[i] += sum_k A(i,k) * B(k, j0)      A(i,k) = TA ? a[k*N + i] : a[i*N + k]
-//                                           B(k,j) = TB ? b[j*N + k] : b[k*N + j]
+//   acc0[i] += sum_k A(i,k) * B(k, j0)      A(i,k) = TA ? a[k*LD + i] : a[i*LD + k]
+//                                           B(k,j) = TB ? b[j*LD + k] : b[k*LD + j]
 template <int N, bool TA, bool TB>
 SY_HD void mm_cols(const double* a, const double* b, int j0, int j1, double* acc0, double* acc1) {
+  constexpr int LD = Layout<N>::LD;
   const bool two = j1 < N;
   const int jj1 = two ? j1 : j0;
 #pragma unroll 1
   for (int k = 0; k < N; ++k) {
-    const double b0 = TB ? b[j0 * N + k] : b[k * N + j0];
-    double b1 = TB ? b[jj1 * N + k] : b[k * N + jj1];
+    const double b0 = TB ? b[j0 * LD + k] : b[k * LD + j0];
+    double b1 = TB ? b[jj1 * LD + k] : b[k * LD + jj1];
     b1 = two ? b1 : 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double av = TA ? a[k * N + i] : a[i * N + k];
+      const double av = TA ? a[k * LD + i] : a[i * LD + k];
       acc0[i] += av * b0;
       acc1[i] += av * b1;
     }
@@ -88,68 +109,78 @@ SY_HD void zero2(double* a, double* b) {
   }
 }
 
-// write owned columns: c[i*N + j] = s * acc[i] (+ diag on the diagonal)
+// write owned columns: c[i*LD + j] = s * acc[i] (+ diag on the diagonal)
 template <int N>
 SY_HD void put_cols(double* c, int j0, int j1, const double* acc0, const double* acc1, double s, double diag) {
+  constexpr int LD = Layout<N>::LD;
 #pragma unroll
-  for (int i = 0; i < N; ++i) c[i * N + j0] = s * acc0[i] + ((i == j0) ? diag : 0.0);
+  for (int i = 0; i < N; ++i) c[i * LD + j0] = s * acc0[i] + ((i == j0) ? diag : 0.0);
   if (j1 < N) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) c[i * N + j1] = s * acc1[i] + ((i == j1) ? diag : 0.0);
+    for (int i = 0; i < N; ++i) c[i * LD + j1] = s * acc1[i] + ((i == j1) ? diag : 0.0);
   }
 }
 
+// c = s * (A op B) (+ diag I) for the owned columns - one stage body
+template <int N, bool TA, bool TB>
+SY_HD void mm_stage(const double* a, const double* b, double* c, int g, double s, double diag) {
+  constexpr int G = Layout<N>::G;
+  double a0[N], a1[N];
+  zero2<N>(a0, a1);
+  mm_cols<N, TA, TB>(a, b, g, g + G, a0, a1);
+  put_cols<N>(c, g, g + G, a0, a1, s, diag);
+}
+
 // Inverse Cholesky factor, cooperative: a (full symmetric, lower part used) -> li (full, upper part
-// zeroed); l = scratch (full), rd = n doubles.  N + 1 stages.
+// zeroed); l = scratch buffer, rd = n doubles.  N + 1 stages.
 template <int N, class Ex>
 SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, double* flag) {
   constexpr int G = Layout<N>::G;
+  constexpr int LD = Layout<N>::LD;
 #pragma unroll 1
   for (int j = 0; j < N; ++j) {
     SY_STAGE_BEGIN(ex)
-    double d = a[j * N + j];
-    for (int k = 0; k < j; ++k) d -= l[j * N + k] * l[j * N + k];
+    double d = a[j * LD + j];
+    for (int k = 0; k < j; ++k) d -= l[j * LD + k] * l[j * LD + k];
     const double r = sy_rsqrt(d);
     for (int i = j + g; i < N; i += G) {
       if (i == j) {
-        l[j * N + j] = d * r;
+        l[j * LD + j] = d * r;
         rd[j] = r;
         if (!(d > 0.0)) *flag = 1.0;
       } else {
-        double s = a[i * N + j];
-        for (int k = 0; k < j; ++k) s -= l[i * N + k] * l[j * N + k];
-        l[i * N + j] = s * r;
+        double s = a[i * LD + j];
+        for (int k = 0; k < j; ++k) s -= l[i * LD + k] * l[j * LD + k];
+        l[i * LD + j] = s * r;
       }
     }
     SY_STAGE_END(ex)
   }
   SY_STAGE_BEGIN(ex)
   for (int c = g; c < N; c += G) {
-    for (int i = 0; i < c; ++i) li[i * N + c] = 0.0;
-    li[c * N + c] = rd[c];
+    for (int i = 0; i < c; ++i) li[i * LD + c] = 0.0;
+    li[c * LD + c] = rd[c];
     for (int i = c + 1; i < N; ++i) {
       double s = 0.0;
-      for (int k = c; k < i; ++k) s += l[i * N + k] * li[k * N + c];
-      li[i * N + c] = -s * rd[i];
+      for (int k = c; k < i; ++k) s += l[i * LD + k] * li[k * LD + c];
+      li[i * LD + c] = -s * rd[i];
     }
   }
   SY_STAGE_END(ex)
 }
 
-// (E + iF)^-1 = U + iV, E SPD (buffer e), F symmetric (buffer f).  Scratch: s0, s1, s2 (full
-// buffers, all distinct from e, f, u, v and from each other; u may not alias anything).
+// (E + iF)^-1 = U + iV, E SPD (buffer e), F symmetric (buffer f).  Scratch: s0, s1, s2.
+// e, f, u, s0, s1, s2 are six distinct buffers; v may alias f (F is dead once T is formed).
 //   lei -> s0 ; T = lei F -> s1 ; S = E + T^T T -> s2 ; lsi -> e (E dead) ; U = lsi^T lsi -> u ;
 //   TU -> s2 ; V = -lei^T TU -> v
 template <int N, class Ex>
 SY_HD void inv_spd_real(Ex& ex, double* e, const double* f, double* u, double* v, double* s0, double* s1, double* s2,
                         double* rd, double* flag) {
   constexpr int G = Layout<N>::G;
+  constexpr int LD = Layout<N>::LD;
   chol_inv<N>(ex, e, s1, s0, rd, flag);  // s1 = scratch L, s0 = lei
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(s0, f, g, g + G, a0, a1);
-  put_cols<N>(s1, g, g + G, a0, a1, 1.0, 0.0);  // T
+  mm_stage<N, false, false>(s0, f, s1, g, 1.0, 0.0);  // T = lei F
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
   double a0[N], a1[N];
@@ -157,28 +188,19 @@ SY_HD void inv_spd_real(Ex& ex, double* e, const double* f, double* u, double* v
   mm_cols<N, true, false>(s1, s1, g, g + G, a0, a1);  // T^T T
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    s2[i * N + g] = a0[i] + e[i * N + g];
-    if (g + G < N) s2[i * N + g + G] = a1[i] + e[i * N + g + G];
+    s2[i * LD + g] = a0[i] + e[i * LD + g];
+    if (g + G < N) s2[i * LD + g + G] = a1[i] + e[i * LD + g + G];
   }
   SY_STAGE_END(ex)
   chol_inv<N>(ex, s2, u, e, rd, flag);  // u = scratch L, e = lsi
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, true, false>(e, e, g, g + G, a0, a1);  // U = lsi^T lsi
-  put_cols<N>(u, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, true, false>(e, e, u, g, 1.0, 0.0);  // U = lsi^T lsi
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(s1, u, g, g + G, a0, a1);  // TU
-  put_cols<N>(s2, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, false, false>(s1, u, s2, g, 1.0, 0.0);  // TU
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, true, false>(s0, s2, g, g + G, a0, a1);  // lei^T TU
-  put_cols<N>(v, g, g + G, a0, a1, -1.0, 0.0);
+  mm_stage<N, true, false>(s0, s2, v, g, -1.0, 0.0);  // V = -lei^T TU
   SY_STAGE_END(ex)
 }
 
@@ -191,50 +213,59 @@ SY_HD void tournament(int r, int k, int* p, int* q) {
     a = NP - 1;
     b = r;
   } else {
-    a = (r + k) % (NP - 1);
-    b = (r - k + (NP - 1)) % (NP - 1);
+    a = r + k;
+    a = a >= NP - 1 ? a - (NP - 1) : a;
+    b = r - k;
+    b = b < 0 ? b + (NP - 1) : b;
   }
   *p = a < b ? a : b;
   *q = a < b ? b : a;
 }
 
-// One-sided Jacobi on the column-major complex matrix (gr, gi) in shared memory (no V).
+// One-sided Jacobi on the column-major complex matrix (gr, gi) in shared memory, column stride LD
+// (no V).  `conv` holds 2 * G not-converged flags, double-buffered by sweep parity.
 template <int N, class Ex>
-SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* worst) {
+SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* conv) {
   constexpr int NP = Layout<N>::NP;
   constexpr int G = Layout<N>::G;
+  constexpr int LD = Layout<N>::LD;
   int sweep = 0;
 #pragma unroll 1
   for (; sweep < kMaxSweeps; ++sweep) {
-    double* wbuf = worst + (sweep & 1) * G;
+    double* wbuf = conv + (sweep & 1) * G;
 #pragma unroll 1
     for (int r = 0; r < NP - 1; ++r) {
       SY_STAGE_BEGIN(ex)
       int p, q;
       tournament<N>(r, g, &p, &q);
-      double ratio = 0.0;
+      double notconv = 0.0;
       if (q < N) {  // q == N is the padding column of an odd n
         double pr[N], pi[N], qr[N], qi[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          pr[i] = gr[p * N + i];
-          pi[i] = gi[p * N + i];
-          qr[i] = gr[q * N + i];
-          qi[i] = gi[q * N + i];
+          pr[i] = gr[p * LD + i];
+          pi[i] = gi[p * LD + i];
+          qr[i] = gr[q * LD + i];
+          qi[i] = gi[q * LD + i];
         }
-        double al = 0.0, be = 0.0, cr = 0.0, ci = 0.0;
+        // two partial sums per quantity: shorter dependency chains
+        double al0 = 0.0, be0 = 0.0, cr0 = 0.0, ci0 = 0.0, al1 = 0.0, be1 = 0.0, cr1 = 0.0, ci1 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          al += pr[i] * pr[i] + pi[i] * pi[i];
-          be += qr[i] * qr[i] + qi[i] * qi[i];
-          cr += pr[i] * qr[i] + pi[i] * qi[i];
-          ci += pr[i] * qi[i] - pi[i] * qr[i];
+          al0 += pr[i] * pr[i];
+          al1 += pi[i] * pi[i];
+          be0 += qr[i] * qr[i];
+          be1 += qi[i] * qi[i];
+          cr0 += pr[i] * qr[i];
+          cr1 += pi[i] * qi[i];
+          ci0 += pr[i] * qi[i];
+          ci1 += pi[i] * qr[i];
         }
+        const double al = al0 + al1, be = be0 + be1, cr = cr0 + cr1, ci = ci0 - ci1;
         const double g2 = cr * cr + ci * ci;
         const double ab = al * be;
-        const bool rot = g2 > reg::kSkipRatio2 * ab;
-        if (rot) {
-          ratio = g2 / ab;
+        if (g2 > reg::kSkipRatio2 * ab) {
+          notconv = (g2 > reg::kStopRatio2 * ab) ? 1.0 : 0.0;
           const double dl = 0.5 * (be - al);
           const double h = dl * dl + g2;
           const double den = fabs(dl) + h * sy_rsqrt(h);
@@ -246,19 +277,19 @@ SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* worst) {
           const double sr = c * tr_, si = c * ti_;
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            gr[p * N + i] = c * pr[i] - (sr * qr[i] + si * qi[i]);
-            gi[p * N + i] = c * pi[i] - (sr * qi[i] - si * qr[i]);
-            gr[q * N + i] = c * qr[i] + (sr * pr[i] - si * pi[i]);
-            gi[q * N + i] = c * qi[i] + (sr * pi[i] + si * pr[i]);
+            gr[p * LD + i] = c * pr[i] - (sr * qr[i] + si * qi[i]);
+            gi[p * LD + i] = c * pi[i] - (sr * qi[i] - si * qr[i]);
+            gr[q * LD + i] = c * qr[i] + (sr * pr[i] - si * pi[i]);
+            gi[q * LD + i] = c * qi[i] + (sr * pi[i] + si * pr[i]);
           }
         }
       }
-      wbuf[g] = (r == 0) ? ratio : (ratio > wbuf[g] ? ratio : wbuf[g]);
+      wbuf[g] = (r == 0) ? notconv : (notconv > wbuf[g] ? notconv : wbuf[g]);
       SY_STAGE_END(ex)
     }
     double w = 0.0;
     for (int k = 0; k < G; ++k) w = wbuf[k] > w ? wbuf[k] : w;
-    const bool more = !(w < reg::kStopRatio2);
+    const bool more = !(w < 0.5);
     if (!ex.any(more)) {
       ++sweep;
       break;
@@ -268,103 +299,189 @@ SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* worst) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Upper half space, one pair, cooperative.  p1 / p2 point at the (2, n, n) rows in global memory.
-// Results are left in the pair's shared-memory region:
-//   sm[DIST], sm[VS .. VS+N) (ascending vvd), sm[FLAG] (status bits as a double)
-//   GRAD:  d dist / d X2 = sm[Q],  d/dY2 = sm[T2],  d/dY1 = sm[P],  d/dX1 = -sm[Q]   (full n x n)
-template <int N, bool GRAD, class Ex>
-SY_HD void upper_pair(Ex& ex, double* sm, const double* p1, const double* p2, int metric, const double* wsum_w) {
+// Metric tail, lanes cooperate: sm[SIG..] holds the (unsorted) singular values.
+//  stage 1: lane k ranks its sigma, computes v_k and dv_k/dsigma_k;
+//  stage 2: every lane sums the n values of v (cheap, identical on all lanes), lane k writes its
+//           backward coefficient (dL/dsigma_k) / sigma_k^3; lane 0 writes dist and the status.
+template <int N, class L, class Ex>
+SY_HD void metric_tail(Ex& ex, double* sm, int metric, const double* wsum_w, int sweeps) {
+  constexpr int G = L::G;
+  SY_STAGE_BEGIN(ex)
+  for (int k = g; k < N; k += G) {
+    const double d = sm[L::SIG + k];
+    int r = 0;
+    for (int j = 0; j < N; ++j) {
+      const double o = sm[L::SIG + j];
+      r += (o < d || (o == d && j < k)) ? 1 : 0;
+    }
+    const double om = 1.0 - d;
+    const bool clamped = om < kEpsF64;
+    const double v = clamped ? log((1.0 + d) / kEpsF64) : log1p(2.0 * d / om);   // siegel_manifold.py:69-70
+    const double dv = clamped ? 1.0 / (1.0 + d) : 2.0 / (om * (1.0 + d));
+    sm[L::VK + k] = v;
+    sm[L::DV + k] = dv;
+    sm[L::RK + k] = (double)r;
+    sm[L::VS + r] = v;
+  }
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  double dist = 0.0;
+  bool above = false;
+  if (metric == kRiem) {
+    for (int k = 0; k < N; ++k) dist += sm[L::VK + k] * sm[L::VK + k];
+    dist = sqrt(dist);
+  }
+  for (int k = 0; k < N; ++k) above = above || (sm[L::SIG + k] > 1.01);
+  double part = 0.0;  // this lane's share of a linear metric
+  for (int k = g; k < N; k += G) {
+    const double sig = sm[L::SIG + k];
+    const double v = sm[L::VK + k];
+    const int r = (int)sm[L::RK + k];
+    double gv;
+    if (metric == kRiem) {
+      gv = dist > 0.0 ? v / dist : 0.0;
+    } else {
+      if (metric == kFone) gv = 1.0;
+      else if (metric == kFinf) gv = (r == N - 1) ? 1.0 : 0.0;
+      else if (metric == kFmin) gv = 2.0 * (double)r;
+      else { gv = wsum_w[r]; gv = gv > 0.0 ? gv : 0.0; }
+      part += gv * v;
+    }
+    // dL/dsigma_k / sigma_k^3   (u_k = g_k / sigma_k, v_k = W^H g_k / sigma_k^2)
+    sm[L::COEF + k] = sig > 1e-150 ? gv * sm[L::DV + k] / (sig * sig * sig) : 0.0;
+  }
+  if (metric != kRiem) sm[L::WORST + g] = part;  // the convergence flags are dead by now
+  if (g == 0) {
+    unsigned st = (sm[L::FLAG] != 0.0) ? kStatusNotPD : 0u;
+    if (sweeps >= kMaxSweeps) st |= kStatusNoConverge;
+    if (above) st |= kStatusTakagiAboveOne;
+    sm[L::FLAG] = (double)st;
+    if (metric == kRiem) sm[L::DIST] = dist;
+  }
+  SY_STAGE_END(ex)
+  if (metric != kRiem) {
+    SY_STAGE_BEGIN(ex)
+    if (g == 0) {
+      double dist = 0.0;
+      for (int k = 0; k < G; ++k) dist += sm[L::WORST + k];
+      sm[L::DIST] = dist;
+    }
+    SY_STAGE_END(ex)
+  }
+  SY_STAGE_BEGIN(ex)
+  if (g == 0) {
+    const double dist = sm[L::DIST];
+    if (!(dist == dist) || dist > 1e300) sm[L::FLAG] = (double)((unsigned)sm[L::FLAG] | kStatusNonFinite);
+  }
+  SY_STAGE_END(ex)
+}
+
+// ---------------------------------------------------------------------------------------------
+// Upper half space, one pair, cooperative, in three parts (fused by upper_pair, or run as three
+// kernels with the state parked in global scratch - see coop_kernels.cuh):
+//   upper_prologue : gather -> LI = chol(Y1)^-1, (A + iC)^-1 = P - iQ        (sm[LI], sm[PBUF], sm[QBUF])
+//   w_from_pq + jacobi + sigma + metric_tail : W -> Takagi values -> vvd, dist, backward coefficients
+//   upper_backward : unit gradients                                          (sm[GX2], sm[GY2], sm[GY1])
+// p1 / p2 point at the (2, n, n) rows in global memory.
+template <int N, class Ex>
+SY_HD void upper_prologue(Ex& ex, double* sm, const double* p1, const double* p2) {
   typedef Layout<N> L;
   constexpr int G = L::G;
   constexpr int NN = L::NN;
+  constexpr int LD = L::LD;
   double* li = sm + L::LI;
-  double* P = sm + L::P;
-  double* Q = sm + L::Q;
-  double* gr = sm + L::GR;
-  double* gi = sm + L::GI;
-  double* t0 = sm + L::T0;
-  double* t1 = sm + L::T1;
-  double* t2 = sm + L::T2;
+  double* a0 = sm + L::A0;
+  double* a1 = sm + L::A1;
+  double* a2 = sm + L::A2;
+  double* a3 = sm + L::A3;
+  double* a4 = sm + L::A4;
+  double* a5 = sm + L::A5;
   double* rd = sm + L::RD;
   double* flag = sm + L::FLAG;
-
-  // ---- load: t0 = D = X2 - X1, t1 = Y1, t2 = Y2 (symmetrised)
+  (void)G; (void)NN; (void)LD; (void)li; (void)a0; (void)a1; (void)a2; (void)a3; (void)a4; (void)a5; (void)rd; (void)flag;
+  // ---- load: a0 = D = X2 - X1, a1 = Y1, a2 = Y2 (symmetrised)
   SY_STAGE_BEGIN(ex)
   if (g == 0) *flag = 0.0;
   for (int e = g; e < NN; e += G) {
-    const int i = e / N, j = e % N, et = j * N + i;
-    t0[e] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
-    t1[e] = 0.5 * (SY_LDG(p1 + NN + e) + SY_LDG(p1 + NN + et));
-    t2[e] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
+    const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
+    a0[s] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
+    a1[s] = 0.5 * (SY_LDG(p1 + NN + e) + SY_LDG(p1 + NN + et));
+    a2[s] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
   }
   SY_STAGE_END(ex)
 
-  chol_inv<N>(ex, t1, Q, li, rd, flag);  // li = chol(Y1)^-1
+  chol_inv<N>(ex, a1, a3, li, rd, flag);  // li = chol(Y1)^-1, scratch a3
 
-  // ---- t1 = li D, gr = li Y2
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(li, t0, g, g + G, a0, a1);
-  put_cols<N>(t1, g, g + G, a0, a1, 1.0, 0.0);
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(li, t2, g, g + G, a0, a1);
-  put_cols<N>(gr, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, false, false>(li, a0, a1, g, 1.0, 0.0);  // a1 = li D
+  mm_stage<N, false, false>(li, a2, a3, g, 1.0, 0.0);  // a3 = li Y2
   SY_STAGE_END(ex)
-  // ---- t0 = -A = -(li D) li^T ; t2 = C = (li Y2) li^T + I
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, true>(t1, li, g, g + G, a0, a1);
-  put_cols<N>(t0, g, g + G, a0, a1, -1.0, 0.0);
-  zero2<N>(a0, a1);
-  mm_cols<N, false, true>(gr, li, g, g + G, a0, a1);
-  put_cols<N>(t2, g, g + G, a0, a1, 1.0, 1.0);
+  mm_stage<N, false, true>(a1, li, a0, g, -1.0, 0.0);  // a0 = -A = -(li D) li^T
+  mm_stage<N, false, true>(a3, li, a2, g, 1.0, 1.0);   // a2 = C = (li Y2) li^T + I
   SY_STAGE_END(ex)
 
-  // ---- (C - iA)^-1 = Q + iP   ->   (A + iC)^-1 = P - iQ
-  inv_spd_real<N>(ex, t2, t0, Q, P, gi, t1, gr, rd, flag);
+  // ---- (C - iA)^-1 = Q + iP  ->  (A + iC)^-1 = P - iQ :   Q = a4, P = a0
+  inv_spd_real<N>(ex, a2, a0, a4, a0, a5, a1, a3, rd, flag);
 
-  // ---- W = (I - 2Q) - 2iP, column-major for the Jacobi
+}
+
+// W = (I - 2Q) - 2iP, column-major with column stride LD (P, Q row-major with leading dimension ldpq)
+template <int N, class Ex>
+SY_HD void w_from_pq(Ex& ex, const double* P, const double* Q, int ldpq, double* gr, double* gi) {
+  typedef LayoutT<N, 2> L;
+  constexpr int G = L::G;
+  constexpr int LD = L::LD;
   SY_STAGE_BEGIN(ex)
-  for (int e = g; e < NN; e += G) {
-    const int c = e / N, r = e % N;
-    gr[e] = ((r == c) ? 1.0 : 0.0) - 2.0 * Q[r * N + c];
-    gi[e] = -2.0 * P[r * N + c];
+  for (int e = g; e < L::NN; e += G) {
+    const int c = e / N, r = e - c * N;
+    gr[c * LD + r] = ((r == c) ? 1.0 : 0.0) - 2.0 * Q[r * ldpq + c];  // generic loads: shared or global
+    gi[c * LD + r] = -2.0 * P[r * ldpq + c];
   }
   SY_STAGE_END(ex)
+}
 
-  const int sweeps = jacobi<N>(ex, gr, gi, sm + L::WORST);
-
-  // ---- singular values, ranking, vector-valued distance, metric (one lane; O(n^2) scalar work)
+// Jacobi + singular values + metric on the G buffers of layout LT (Layout<N> or LayoutJ<N>)
+template <int N, class LT, class Ex>
+SY_HD void spectrum(Ex& ex, double* sm, int metric, const double* wsum_w) {
+  constexpr int G = LT::G;
+  constexpr int LD = LT::LD;
+  double* gr = sm + LT::GR;
+  double* gi = sm + LT::GI;
+  const int sweeps = jacobi<N>(ex, gr, gi, sm + LT::WORST);
   SY_STAGE_BEGIN(ex)
   for (int k = g; k < N; k += G) {
-    double a = 0.0;
-    for (int i = 0; i < N; ++i) a += gr[k * N + i] * gr[k * N + i] + gi[k * N + i] * gi[k * N + i];
-    sm[L::SIG + k] = sqrt(a);
-  }
-  SY_STAGE_END(ex)
-  SY_STAGE_BEGIN(ex)
-  if (g == 0) {
-    double sig[N], v[N], gsig[N];
-    int rank[N];
-    unsigned st = (*flag != 0.0) ? kStatusNotPD : 0u;
-    if (sweeps >= kMaxSweeps) st |= kStatusNoConverge;
-    for (int k = 0; k < N; ++k) sig[k] = sm[L::SIG + k];
-    const double dist = loc::metric_reduce<N>(sig, metric, wsum_w, rank, v, gsig, &st);
-    if (!(dist == dist) || dist > 1e300) st |= kStatusNonFinite;
-    for (int k = 0; k < N; ++k) {
-      sm[L::VS + rank[k]] = v[k];
-      // dL/dsigma_k / sigma_k^3   (v_k = W^H g_k / sigma_k^2, u_k = g_k / sigma_k)
-      sm[L::COEF + k] = sig[k] > 1e-150 ? gsig[k] / (sig[k] * sig[k] * sig[k]) : 0.0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < N; ++i) {
+      s0 += gr[k * LD + i] * gr[k * LD + i];
+      s1 += gi[k * LD + i] * gi[k * LD + i];
     }
-    sm[L::DIST] = dist;
-    *flag = (double)st;
+    sm[LT::SIG + k] = sqrt(s0 + s1);
   }
   SY_STAGE_END(ex)
-  if (!GRAD) return;
+  metric_tail<N, LT>(ex, sm, metric, wsum_w, sweeps);
+}
 
-  // ---- F = sum_k coef_k g_k g_k^H  (Hermitian):  t0 = Re F, t1 = Im F
+// backward: needs sm[LI], P = sm[PBUF], Q = sm[QBUF], G = (sm[GR], sm[GI]) column-major, sm[COEF]
+template <int N, class Ex>
+SY_HD void upper_backward(Ex& ex, double* sm, const double* p1, const double* p2) {
+  typedef Layout<N> L;
+  constexpr int G = L::G;
+  constexpr int NN = L::NN;
+  constexpr int LD = L::LD;
+  double* li = sm + L::LI;
+  double* a0 = sm + L::A0;
+  double* a1 = sm + L::A1;
+  double* a2 = sm + L::A2;
+  double* a3 = sm + L::A3;
+  double* a4 = sm + L::A4;
+  double* a5 = sm + L::A5;
+  double* rd = sm + L::RD;
+  double* flag = sm + L::FLAG;
+  (void)G; (void)NN; (void)LD; (void)li; (void)a0; (void)a1; (void)a2; (void)a3; (void)a4; (void)a5; (void)rd; (void)flag;
+  double* P = a0;
+  double* Q = a4;
+  // ---- F = sum_k coef_k g_k g_k^H  (Hermitian):  a3 = Re F, a5 = Im F
   SY_STAGE_BEGIN(ex)
   const int j0 = g, j1 = g + G;
   const bool two = j1 < N;
@@ -375,178 +492,234 @@ SY_HD void upper_pair(Ex& ex, double* sm, const double* p1, const double* p2, in
 #pragma unroll 1
   for (int k = 0; k < N; ++k) {
     const double c = sm[L::COEF + k];
-    const double b0r = c * gr[k * N + j0], b0i = c * gi[k * N + j0];
-    const double b1r = two ? c * gr[k * N + jj1] : 0.0, b1i = two ? c * gi[k * N + jj1] : 0.0;
+    const double b0r = c * a1[k * LD + j0], b0i = c * a2[k * LD + j0];
+    const double b1r = two ? c * a1[k * LD + jj1] : 0.0, b1i = two ? c * a2[k * LD + jj1] : 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double ar = gr[k * N + i], ai = gi[k * N + i];
-      // g_k[i] * conj(g_k[j])
-      fr0[i] += ar * b0r + ai * b0i;
+      const double ar = a1[k * LD + i], ai = a2[k * LD + i];
+      fr0[i] += ar * b0r + ai * b0i;  // g_k[i] * conj(g_k[j])
       fi0[i] += ai * b0r - ar * b0i;
       fr1[i] += ar * b1r + ai * b1i;
       fi1[i] += ai * b1r - ar * b1i;
     }
   }
-  put_cols<N>(t0, j0, j1, fr0, fr1, 1.0, 0.0);
-  put_cols<N>(t1, j0, j1, fi0, fi1, 1.0, 0.0);
+  put_cols<N>(a3, j0, j1, fr0, fr1, 1.0, 0.0);
+  put_cols<N>(a5, j0, j1, fi0, fi1, 1.0, 0.0);
   SY_STAGE_END(ex)
 
-  // ---- GW = F W,  W = (I - 2Q) - 2iP   ->  gr = Re GW, gi = Im GW (row-major from here on)
-  //      F W = F - 2 F (Q + iP):   Re = Fr - 2 (Fr Q - Fi P),  Im = Fi - 2 (Fr P + Fi Q)
+  // ---- GW = F W = F - 2 F (Q + iP):  a1 = Re = Fr - 2 (Fr Q - Fi P),  a2 = Im = Fi - 2 (Fr P + Fi Q)
   SY_STAGE_BEGIN(ex)
   const int j0 = g, j1 = g + G;
-  double a0[N], a1[N], b0[N], b1[N];
-  zero2<N>(a0, a1);
-  zero2<N>(b0, b1);
-  mm_cols<N, false, false>(t0, Q, j0, j1, a0, a1);  // Fr Q
-  mm_cols<N, false, false>(t0, P, j0, j1, b0, b1);  // Fr P
-  double c0[N], c1[N], d0[N], d1[N];
-  zero2<N>(c0, c1);
-  zero2<N>(d0, d1);
-  mm_cols<N, false, false>(t1, P, j0, j1, c0, c1);  // Fi P
-  mm_cols<N, false, false>(t1, Q, j0, j1, d0, d1);  // Fi Q
+  double x0[N], x1[N], y0[N], y1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  mm_cols<N, false, false>(a3, Q, j0, j1, x0, x1);  // Fr Q
+  mm_cols<N, false, false>(a3, P, j0, j1, y0, y1);  // Fr P
+  double z0[N], z1[N], w0[N], w1[N];
+  zero2<N>(z0, z1);
+  zero2<N>(w0, w1);
+  mm_cols<N, false, false>(a5, P, j0, j1, z0, z1);  // Fi P
+  mm_cols<N, false, false>(a5, Q, j0, j1, w0, w1);  // Fi Q
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    gr[i * N + j0] = t0[i * N + j0] - 2.0 * (a0[i] - c0[i]);
-    gi[i * N + j0] = t1[i * N + j0] - 2.0 * (b0[i] + d0[i]);
+    a1[i * LD + j0] = a3[i * LD + j0] - 2.0 * (x0[i] - z0[i]);
+    a2[i * LD + j0] = a5[i * LD + j0] - 2.0 * (y0[i] + w0[i]);
     if (j1 < N) {
-      gr[i * N + j1] = t0[i * N + j1] - 2.0 * (a1[i] - c1[i]);
-      gi[i * N + j1] = t1[i * N + j1] - 2.0 * (b1[i] + d1[i]);
+      a1[i * LD + j1] = a3[i * LD + j1] - 2.0 * (x1[i] - z1[i]);
+      a2[i * LD + j1] = a5[i * LD + j1] - 2.0 * (y1[i] + w1[i]);
     }
   }
   SY_STAGE_END(ex)
 
-  // ---- G_N = 2i sym(GW) = i (GW + GW^T):  t0 = Re = -(GWi + GWi^T),  t1 = Im = GWr + GWr^T
+  // ---- G_N = 2i sym(GW) = i (GW + GW^T):  a3 = Re = -(GWi + GWi^T),  a5 = Im = GWr + GWr^T
   SY_STAGE_BEGIN(ex)
   for (int e = g; e < NN; e += G) {
-    const int i = e / N, j = e % N, et = j * N + i;
-    t0[e] = -(gi[e] + gi[et]);
-    t1[e] = gr[e] + gr[et];
+    const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+    a3[s] = -(a2[s] + a2[t]);
+    a5[s] = a1[s] + a1[t];
   }
   SY_STAGE_END(ex)
 
-  // ---- Tm = conj(N) G_N, conj(N) = P + iQ:  gr = P GNr - Q GNi,  gi = P GNi + Q GNr
+  // ---- Tm = conj(N) G_N, conj(N) = P + iQ:  a1 = P GNr - Q GNi,  a2 = P GNi + Q GNr
   SY_STAGE_BEGIN(ex)
   const int j0 = g, j1 = g + G;
-  double a0[N], a1[N], b0[N], b1[N], c0[N], c1[N], d0[N], d1[N];
-  zero2<N>(a0, a1);
-  zero2<N>(b0, b1);
-  zero2<N>(c0, c1);
-  zero2<N>(d0, d1);
-  mm_cols<N, false, false>(P, t0, j0, j1, a0, a1);
-  mm_cols<N, false, false>(Q, t1, j0, j1, b0, b1);
-  mm_cols<N, false, false>(P, t1, j0, j1, c0, c1);
-  mm_cols<N, false, false>(Q, t0, j0, j1, d0, d1);
+  double x0[N], x1[N], y0[N], y1[N], z0[N], z1[N], w0[N], w1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  zero2<N>(z0, z1);
+  zero2<N>(w0, w1);
+  mm_cols<N, false, false>(P, a3, j0, j1, x0, x1);
+  mm_cols<N, false, false>(Q, a5, j0, j1, y0, y1);
+  mm_cols<N, false, false>(P, a5, j0, j1, z0, z1);
+  mm_cols<N, false, false>(Q, a3, j0, j1, w0, w1);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    gr[i * N + j0] = a0[i] - b0[i];
-    gi[i * N + j0] = c0[i] + d0[i];
+    a1[i * LD + j0] = x0[i] - y0[i];
+    a2[i * LD + j0] = z0[i] + w0[i];
     if (j1 < N) {
-      gr[i * N + j1] = a1[i] - b1[i];
-      gi[i * N + j1] = c1[i] + d1[i];
+      a1[i * LD + j1] = x1[i] - y1[i];
+      a2[i * LD + j1] = z1[i] + w1[i];
     }
   }
   SY_STAGE_END(ex)
 
-  // ---- G_M = -Tm conj(N):  t0 = G_A = -(Tmr P - Tmi Q),  t1 = G_B = -(Tmr Q + Tmi P)
+  // ---- G_M = -Tm conj(N):  a3 = G_A = -(Tmr P - Tmi Q),  a5 = G_B = -(Tmr Q + Tmi P)
   SY_STAGE_BEGIN(ex)
   const int j0 = g, j1 = g + G;
-  double a0[N], a1[N], b0[N], b1[N], c0[N], c1[N], d0[N], d1[N];
-  zero2<N>(a0, a1);
-  zero2<N>(b0, b1);
-  zero2<N>(c0, c1);
-  zero2<N>(d0, d1);
-  mm_cols<N, false, false>(gr, P, j0, j1, a0, a1);
-  mm_cols<N, false, false>(gi, Q, j0, j1, b0, b1);
-  mm_cols<N, false, false>(gr, Q, j0, j1, c0, c1);
-  mm_cols<N, false, false>(gi, P, j0, j1, d0, d1);
+  double x0[N], x1[N], y0[N], y1[N], z0[N], z1[N], w0[N], w1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  zero2<N>(z0, z1);
+  zero2<N>(w0, w1);
+  mm_cols<N, false, false>(a1, P, j0, j1, x0, x1);
+  mm_cols<N, false, false>(a2, Q, j0, j1, y0, y1);
+  mm_cols<N, false, false>(a1, Q, j0, j1, z0, z1);
+  mm_cols<N, false, false>(a2, P, j0, j1, w0, w1);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    t0[i * N + j0] = -(a0[i] - b0[i]);
-    t1[i * N + j0] = -(c0[i] + d0[i]);
+    a3[i * LD + j0] = -(x0[i] - y0[i]);
+    a5[i * LD + j0] = -(z0[i] + w0[i]);
     if (j1 < N) {
-      t0[i * N + j1] = -(a1[i] - b1[i]);
-      t1[i * N + j1] = -(c1[i] + d1[i]);
+      a3[i * LD + j1] = -(x1[i] - y1[i]);
+      a5[i * LD + j1] = -(z1[i] + w1[i]);
     }
   }
   SY_STAGE_END(ex)
 
-  // ---- symmetrise G_A, G_B in place is not possible inside one stage: use them through sym access
-  //      below (0.5 (g[i][j] + g[j][i])) only where symmetry matters (it does not: every use is a
-  //      congruence or a product whose result is symmetrised at the end).
-
-  // ---- reload D -> Q, Y2 -> P (P, Q are dead)
+  // ---- reload D -> a0, Y2 -> a4 (P, Q are dead)
   SY_STAGE_BEGIN(ex)
   for (int e = g; e < NN; e += G) {
-    const int i = e / N, j = e % N, et = j * N + i;
-    Q[e] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
-    P[e] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
+    const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
+    a0[s] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
+    a4[s] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
   }
   SY_STAGE_END(ex)
-  // ---- gr = T1 = li D, gi = T2 = li Y2
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(li, Q, g, g + G, a0, a1);
-  put_cols<N>(gr, g, g + G, a0, a1, 1.0, 0.0);
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(li, P, g, g + G, a0, a1);
-  put_cols<N>(gi, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, false, false>(li, a0, a1, g, 1.0, 0.0);  // a1 = T1 = li D
+  mm_stage<N, false, false>(li, a4, a2, g, 1.0, 0.0);  // a2 = T2 = li Y2
   SY_STAGE_END(ex)
-  // ---- t2 = G_Li = 2 (G_A T1 + G_B T2)   (only its lower triangle is used)
+  // ---- a0 = G_Li = 2 (G_A T1 + G_B T2)   (only its lower triangle is used)
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(t0, gr, g, g + G, a0, a1);
-  mm_cols<N, false, false>(t1, gi, g, g + G, a0, a1);
-  put_cols<N>(t2, g, g + G, a0, a1, 2.0, 0.0);
+  double x0[N], x1[N];
+  zero2<N>(x0, x1);
+  mm_cols<N, false, false>(a3, a1, g, g + G, x0, x1);
+  mm_cols<N, false, false>(a5, a2, g, g + G, x0, x1);
+  put_cols<N>(a0, g, g + G, x0, x1, 2.0, 0.0);
   SY_STAGE_END(ex)
-  // ---- Q = K_s: 0.5 * tril(G_Li li^T) mirrored to a full symmetric matrix
+  // ---- a4 = K_s: 0.5 * tril(G_Li li^T) mirrored to a full symmetric matrix
   SY_STAGE_BEGIN(ex)
   for (int e = g; e < NN; e += G) {
-    const int i = e / N, j = e % N;
+    const int i = e / N, j = e - i * N;
     if (i >= j) {
       double a = 0.0;
-      for (int k = 0; k <= j; ++k) a += t2[i * N + k] * li[j * N + k];
-      Q[i * N + j] = 0.5 * a;
-      Q[j * N + i] = 0.5 * a;
+      for (int k = 0; k <= j; ++k) a += a0[i * LD + k] * li[j * LD + k];
+      a4[i * LD + j] = 0.5 * a;
+      a4[j * LD + i] = 0.5 * a;
     }
   }
   SY_STAGE_END(ex)
-  // ---- gr = K_s li
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(Q, li, g, g + G, a0, a1);
-  put_cols<N>(gr, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, false, false>(a4, li, a1, g, 1.0, 0.0);  // a1 = K_s li
   SY_STAGE_END(ex)
-  // ---- P = G_Y1 = -li^T (K_s li)
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, true, false>(li, gr, g, g + G, a0, a1);
-  put_cols<N>(P, g, g + G, a0, a1, -1.0, 0.0);
+  mm_stage<N, true, false>(li, a1, a0, g, -1.0, 0.0);  // a0 = G_Y1 = -li^T K_s li
   SY_STAGE_END(ex)
-  // ---- gr = G_A li, gi = G_B li
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(t0, li, g, g + G, a0, a1);
-  put_cols<N>(gr, g, g + G, a0, a1, 1.0, 0.0);
-  zero2<N>(a0, a1);
-  mm_cols<N, false, false>(t1, li, g, g + G, a0, a1);
-  put_cols<N>(gi, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, false, false>(a3, li, a1, g, 1.0, 0.0);  // a1 = G_A li
+  mm_stage<N, false, false>(a5, li, a2, g, 1.0, 0.0);  // a2 = G_B li
   SY_STAGE_END(ex)
-  // ---- Q = G_X2 = li^T (G_A li), t2 = G_Y2 = li^T (G_B li)
   SY_STAGE_BEGIN(ex)
-  double a0[N], a1[N];
-  zero2<N>(a0, a1);
-  mm_cols<N, true, false>(li, gr, g, g + G, a0, a1);
-  put_cols<N>(Q, g, g + G, a0, a1, 1.0, 0.0);
-  zero2<N>(a0, a1);
-  mm_cols<N, true, false>(li, gi, g, g + G, a0, a1);
-  put_cols<N>(t2, g, g + G, a0, a1, 1.0, 0.0);
+  mm_stage<N, true, false>(li, a1, a4, g, 1.0, 0.0);  // a4 = G_X2 = li^T G_A li
+  mm_stage<N, true, false>(li, a2, a3, g, 1.0, 0.0);  // a3 = G_Y2 = li^T G_B li
   SY_STAGE_END(ex)
+}
+
+// park / fetch one n x n buffer (leading dimension LD in shared memory, compact n*n in global scratch)
+template <int N, class Ex>
+SY_HD void park(Ex& ex, const double* smbuf, double* gbuf) {
+  typedef LayoutT<N, 2> L;
+  SY_STAGE_BEGIN(ex)
+  for (int e = g; e < L::NN; e += L::G) {
+    const int i = e / N, j = e - i * N;
+    gbuf[e] = smbuf[i * L::LD + j];
+  }
+  SY_STAGE_END(ex)
+}
+template <int N, class Ex>
+SY_HD void fetch(Ex& ex, const double* gbuf, double* smbuf) {
+  typedef LayoutT<N, 2> L;
+  SY_STAGE_BEGIN(ex)
+  for (int e = g; e < L::NN; e += L::G) {
+    const int i = e / N, j = e - i * N;
+    smbuf[i * L::LD + j] = gbuf[e];
+  }
+  SY_STAGE_END(ex)
+}
+
+// scratch layout of the split path, per chunk of `cap` pairs (doubles): five n x n planes + coef
+template <int N>
+struct Scratch {
+  static constexpr int64_t kPerPair = 5 * N * N + N;
+  static SY_HD double* li(double* s, int64_t cap, int64_t p) { return s + (0 * cap + p) * N * N; }
+  static SY_HD double* pb(double* s, int64_t cap, int64_t p) { return s + (1 * cap + p) * N * N; }
+  static SY_HD double* qb(double* s, int64_t cap, int64_t p) { return s + (2 * cap + p) * N * N; }
+  static SY_HD double* gr(double* s, int64_t cap, int64_t p) { return s + (3 * cap + p) * N * N; }
+  static SY_HD double* gi(double* s, int64_t cap, int64_t p) { return s + (4 * cap + p) * N * N; }
+  static SY_HD double* coef(double* s, int64_t cap, int64_t p) { return s + 5 * cap * N * N + p * N; }
+};
+
+// split path, part 1: prologue, then park LI, P, Q
+template <int N, class Ex>
+SY_HD void split_prologue(Ex& ex, double* sm, const double* p1, const double* p2, double* scratch, int64_t cap,
+                          int64_t slot) {
+  typedef Layout<N> L;
+  upper_prologue<N>(ex, sm, p1, p2);
+  park<N>(ex, sm + L::LI, Scratch<N>::li(scratch, cap, slot));
+  park<N>(ex, sm + L::PBUF, Scratch<N>::pb(scratch, cap, slot));
+  park<N>(ex, sm + L::QBUF, Scratch<N>::qb(scratch, cap, slot));
+}
+// part 2: W from the parked P, Q; Jacobi; metric; park G (column-major planes) and the coefficients
+template <int N, bool GRAD, class Ex>
+SY_HD void split_spectrum(Ex& ex, double* sm, int metric, const double* wsum_w, double* scratch, int64_t cap,
+                          int64_t slot) {
+  typedef LayoutJ<N> L;
+  SY_STAGE_BEGIN(ex)
+  if (g == 0) sm[L::FLAG] = 0.0;
+  SY_STAGE_END(ex)
+  w_from_pq<N>(ex, Scratch<N>::pb(scratch, cap, slot), Scratch<N>::qb(scratch, cap, slot), N, sm + L::GR, sm + L::GI);
+  spectrum<N, L>(ex, sm, metric, wsum_w);
+  if (GRAD) {
+    park<N>(ex, sm + L::GR, Scratch<N>::gr(scratch, cap, slot));
+    park<N>(ex, sm + L::GI, Scratch<N>::gi(scratch, cap, slot));
+    SY_STAGE_BEGIN(ex)
+    for (int k = g; k < N; k += L::G) Scratch<N>::coef(scratch, cap, slot)[k] = sm[L::COEF + k];
+    SY_STAGE_END(ex)
+  }
+}
+// part 3: fetch everything, backward
+template <int N, class Ex>
+SY_HD void split_backward(Ex& ex, double* sm, const double* p1, const double* p2, double* scratch, int64_t cap,
+                          int64_t slot) {
+  typedef Layout<N> L;
+  fetch<N>(ex, Scratch<N>::li(scratch, cap, slot), sm + L::LI);
+  fetch<N>(ex, Scratch<N>::pb(scratch, cap, slot), sm + L::PBUF);
+  fetch<N>(ex, Scratch<N>::qb(scratch, cap, slot), sm + L::QBUF);
+  fetch<N>(ex, Scratch<N>::gr(scratch, cap, slot), sm + L::GR);
+  fetch<N>(ex, Scratch<N>::gi(scratch, cap, slot), sm + L::GI);
+  SY_STAGE_BEGIN(ex)
+  for (int k = g; k < N; k += L::G) sm[L::COEF + k] = Scratch<N>::coef(scratch, cap, slot)[k];
+  SY_STAGE_END(ex)
+  upper_backward<N>(ex, sm, p1, p2);
+}
+
+// fused: everything in one go (what the single-kernel path and the forward-only path use)
+template <int N, bool GRAD, class Ex>
+SY_HD void upper_pair(Ex& ex, double* sm, const double* p1, const double* p2, int metric, const double* wsum_w) {
+  typedef Layout<N> L;
+  upper_prologue<N>(ex, sm, p1, p2);
+  w_from_pq<N>(ex, sm + L::PBUF, sm + L::QBUF, L::LD, sm + L::GR, sm + L::GI);
+  spectrum<N, L>(ex, sm, metric, wsum_w);
+  if (GRAD) upper_backward<N>(ex, sm, p1, p2);
 }
 
 }  // namespace coop

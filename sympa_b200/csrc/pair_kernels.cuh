@@ -32,6 +32,9 @@ struct PairArgs {
   double* grad_wsum_w;
   double* grad_scale;
   double* loss_out;
+  // optional global scratch for the three-kernel split path (upper, n > SY_REG_MAX_N)
+  double* scratch;
+  int64_t scratch_pairs;
 };
 
 // launch the pair kernel for matrix size N; defined (explicitly instantiated) in pair_kernels_n.cu
@@ -248,12 +251,15 @@ static int launch_one(const PairArgs& a, cudaStream_t s) {
 
 template <int N, int KIND, int MODE>
 static int launch_coop(const PairArgs& a, cudaStream_t s);  // coop_kernels.cuh
+template <int N, int MODE>
+static int launch_split(const PairArgs& a, double* scratch, int64_t cap, cudaStream_t s);
 
 // kernel selection: one pair per thread in registers for n <= SY_REG_MAX_N; warp-cooperative shared
 // memory kernel for the larger upper-half sizes; rolled per-thread fallback otherwise.
 template <int N, int KIND, int MODE>
 static int launch_any(const PairArgs& a, cudaStream_t s) {
   if constexpr (KIND == kUpper && (N > SY_REG_MAX_N)) {
+    if (a.scratch != nullptr && a.scratch_pairs > 0) return launch_split<N, MODE>(a, a.scratch, a.scratch_pairs, s);
     return launch_coop<N, KIND, MODE>(a, s);
   } else {
     return launch_one<N, KIND, MODE>(a, s);

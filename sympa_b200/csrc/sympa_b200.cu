@@ -162,9 +162,43 @@ int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs) {
   return 2 * num_pairs * (int64_t)point_doubles(kind, n) * (int64_t)sizeof(double);
 }
 
+static const int64_t kSplitChunkPairs = 32768;  // scratch per chunk stays L2-resident (n = 10: 134 MB .. n = 5: 35 MB)
+static const int64_t kSplitMinPairs = 2048;     // below this the single-kernel path is used
+
+static bool uses_scratch(int kind, int n) { return kind == SYMPA_KIND_UPPER && n > SY_REG_MAX_N; }
+static int64_t scratch_per_pair_bytes(int n) { return (int64_t)(5 * n * n + n) * (int64_t)sizeof(double); }
+static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs * (int64_t)(1 + n) * (int64_t)sizeof(double); }
+
+int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs) {
+  if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N || num_pairs < 0) return -1;
+  if (!uses_scratch(kind, n) || num_pairs < kSplitMinPairs) return 0;
+  const int64_t cap = num_pairs < kSplitChunkPairs ? num_pairs : kSplitChunkPairs;
+  return cap * scratch_per_pair_bytes(n) + scratch_tail_bytes(n, num_pairs);
+}
+
+// carve the caller's scratch: [chunk planes][dist: num_pairs][vvd: num_pairs * n]
+static void setup_scratch(PairArgs* a, int kind, int n, double* scratch, int64_t scratch_bytes, bool need_tail) {
+  a->scratch = nullptr;
+  a->scratch_pairs = 0;
+  if (scratch == nullptr || !uses_scratch(kind, n) || a->num_pairs < kSplitMinPairs) return;
+  const int64_t tail = scratch_tail_bytes(n, a->num_pairs);
+  if (scratch_bytes <= tail) return;
+  int64_t cap = (scratch_bytes - tail) / scratch_per_pair_bytes(n);
+  if (cap > a->num_pairs) cap = a->num_pairs;
+  if (cap < kSplitMinPairs) return;
+  a->scratch = scratch;
+  a->scratch_pairs = cap;
+  if (need_tail) {
+    double* t = scratch + cap * (scratch_per_pair_bytes(n) / (int64_t)sizeof(double));
+    if (a->dist_out == nullptr) a->dist_out = t;
+    if (a->vvd_out == nullptr && a->metric == SYMPA_METRIC_WSUM) a->vvd_out = t + a->num_pairs;
+  }
+}
+
 int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs, const double* z1, const double* z2,
                        const double* table, int64_t num_rows, const int64_t* idx, const double* wsum_w,
-                       double* dist_out, double* vvd_out, double* saved_state, unsigned int* status, void* stream) {
+                       double* dist_out, double* vvd_out, double* saved_state, double* scratch,
+                       int64_t scratch_bytes, unsigned int* status, void* stream) {
   if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
   const bool mat = z1 != nullptr || z2 != nullptr;
   const bool tab = table != nullptr || idx != nullptr;
@@ -190,6 +224,7 @@ int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs, const dou
     a.gz1 = saved_state;
     a.gz2 = saved_state + num_pairs * (int64_t)point_doubles(kind, n);
   }
+  setup_scratch(&a, kind, n, scratch, scratch_bytes, false);
   return launch_n(n, kind, saved_state != nullptr ? kModeFwdSave : kModeFwd, a, (cudaStream_t)stream);
 }
 
@@ -239,7 +274,8 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const do
 int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs, const double* table, int64_t num_rows,
                           const int64_t* idx, const double* graph_dist, double scale, const double* wsum_w,
                           double* grad_table, double* grad_wsum_w, double* grad_scale, double* loss_out,
-                          double* dist_out, unsigned int* status, void* stream) {
+                          double* dist_out, double* scratch, int64_t scratch_bytes, unsigned int* status,
+                          void* stream) {
   if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
   if (table == nullptr || idx == nullptr || graph_dist == nullptr || grad_table == nullptr || num_rows <= 0)
     return SYMPA_ERR_BAD_ARG;
@@ -260,6 +296,7 @@ int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs, const 
   a.grad_wsum_w = grad_wsum_w;
   a.grad_scale = grad_scale;
   a.loss_out = loss_out;
+  setup_scratch(&a, kind, n, scratch, scratch_bytes, true);
   return launch_n(n, kind, kModeStep, a, (cudaStream_t)stream);
 }
 

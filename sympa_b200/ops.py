@@ -8,6 +8,7 @@ import torch
 from . import _lib
 
 _status_words = {}
+_scratch = {}
 
 
 def _ptr(t):
@@ -26,6 +27,20 @@ def status_word(device):
         w = torch.zeros(1, dtype=torch.int32, device=device)
         _status_words[key] = w
     return w
+
+
+def scratch_for(kind, n, num_pairs, device):
+    """Per-device scratch buffer (grown on demand, reused by every call on that device - calls are
+    stream-ordered) for the three-kernel path of the larger matrix sizes."""
+    nbytes = _lib.load().sympa_scratch_bytes(_lib.KIND[kind], n, num_pairs)
+    if nbytes <= 0:
+        return None, 0
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        _scratch[key] = buf
+    return buf, buf.numel() * 8
 
 
 def check_status(device=None, reset=True):
@@ -101,10 +116,11 @@ def forward_raw(kind, metric, z1=None, z2=None, table=None, idx=None, wsum_w=Non
         if want_grad:
             nbytes = lib.sympa_workspace_bytes(_lib.KIND[kind], n, b)
             saved = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+        scratch, scratch_bytes = scratch_for(kind, n, b, dev)
         _lib.check(lib.sympa_dist_forward(
             _lib.KIND[kind], n, _lib.METRIC[metric], b, _ptr(z1), _ptr(z2), _ptr(table),
             0 if table is None else table.shape[0], _ptr(idx), _ptr(wsum_w), _ptr(dist), _ptr(vvd), _ptr(saved),
-            _ptr(status_word(dev)), _stream()))
+            _ptr(scratch), scratch_bytes, _ptr(status_word(dev)), _stream()))
     return dist, vvd, saved
 
 
@@ -213,10 +229,11 @@ def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsu
     else:
         wsum_w = None
     with torch.cuda.device(dev):
+        scratch, scratch_bytes = scratch_for(kind, n, idx.shape[0], dev)
         if loss_out is None:
             loss_out = torch.zeros(1, dtype=torch.float64, device=dev)
         _lib.check(lib.sympa_distortion_step(
             _lib.KIND[kind], n, _lib.METRIC[metric], idx.shape[0], _ptr(table), table.shape[0], _ptr(idx),
             _ptr(graph_dist), float(scale), _ptr(wsum_w), _ptr(grad_table), _ptr(grad_wsum_w), _ptr(grad_scale),
-            _ptr(loss_out), _ptr(dist_out), _ptr(status_word(dev)), _stream()))
+            _ptr(loss_out), _ptr(dist_out), _ptr(scratch), scratch_bytes, _ptr(status_word(dev)), _stream()))
     return loss_out

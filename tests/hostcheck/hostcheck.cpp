@@ -4,6 +4,7 @@
 //   variant 0 = namespace sympa::reg (unrolled, what the kernels use for n <= 4)
 //   variant 1 = namespace sympa::loc (rolled loops, per-thread fallback)
 //   variant 2 = namespace sympa::coop (warp-cooperative shared-memory kernels, lanes emulated sequentially)
+//   variant 3 = the same, split in three parts with the state parked in (poisoned) global scratch
 #include "../../sympa_b200/csrc/pair_math.cuh"
 #include "../../sympa_b200/csrc/coop_math.cuh"
 #include <vector>
@@ -61,33 +62,53 @@ using namespace sympa;
 HC_RUN(reg)
 HC_RUN(loc)
 
-template <int N>
+template <int N, bool SPLIT>
 static void run_coop(int kind, int metric, int64_t b, const double* z1, const double* z2, const double* w, int grad,
                      double* dist, double* vvd, double* g1, double* g2, unsigned* status) {
   typedef coop::Layout<N> L;
+  typedef coop::LayoutJ<N> LJ;
   const int per = 2 * N * N;
-  std::vector<double> sm(L::kDoubles);
+  std::vector<double> sm(L::kDoubles), smj(LJ::kDoubles);
+  const int64_t cap = 3;  // scratch capacity in pairs; the slot rotates so that the indexing is exercised
+  std::vector<double> scratch(coop::Scratch<N>::kPerPair * cap);
   coop::HostExec ex{L::G};
   for (int64_t p = 0; p < b; ++p) {
     for (auto& x : sm) x = -7.0e300;  // poison: any read of an unwritten slot shows up
-    if (grad)
-      coop::upper_pair<N, true>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
-    else
-      coop::upper_pair<N, false>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
-    dist[p] = sm[L::DIST];
-    for (int k = 0; k < N; ++k) vvd[p * N + k] = sm[L::VS + k];
-    *status |= (unsigned)sm[L::FLAG];
+    for (auto& x : smj) x = -7.0e300;
+    if (!SPLIT) {
+      if (grad)
+        coop::upper_pair<N, true>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+      else
+        coop::upper_pair<N, false>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+      dist[p] = sm[L::DIST];
+      for (int k = 0; k < N; ++k) vvd[p * N + k] = sm[L::VS + k];
+      *status |= (unsigned)sm[L::FLAG];
+    } else {
+      for (auto& x : scratch) x = -7.0e300;
+      const int64_t slot = p % cap;
+      coop::split_prologue<N>(ex, sm.data(), z1 + p * per, z2 + p * per, scratch.data(), cap, slot);
+      if (sm[L::FLAG] != 0.0) *status |= kStatusNotPD;
+      for (auto& x : sm) x = -7.0e300;
+      if (grad)
+        coop::split_spectrum<N, true>(ex, smj.data(), metric, w, scratch.data(), cap, slot);
+      else
+        coop::split_spectrum<N, false>(ex, smj.data(), metric, w, scratch.data(), cap, slot);
+      dist[p] = smj[LJ::DIST];
+      for (int k = 0; k < N; ++k) vvd[p * N + k] = smj[LJ::VS + k];
+      *status |= (unsigned)smj[LJ::FLAG];
+      if (grad) coop::split_backward<N>(ex, sm.data(), z1 + p * per, z2 + p * per, scratch.data(), cap, slot);
+    }
     if (grad) {
-      const double* gx2 = &sm[L::Q];
-      const double* gy2 = &sm[L::T2];
-      const double* gy1 = &sm[L::P];
+      const double* gx2 = &sm[L::GX2];
+      const double* gy2 = &sm[L::GY2];
+      const double* gy1 = &sm[L::GY1];
       for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) {
-          const int e = i * N + j, et = j * N + i;
-          g2[p * per + e] = 0.5 * (gx2[e] + gx2[et]);
-          g2[p * per + N * N + e] = 0.5 * (gy2[e] + gy2[et]);
-          g1[p * per + e] = -0.5 * (gx2[e] + gx2[et]);
-          g1[p * per + N * N + e] = 0.5 * (gy1[e] + gy1[et]);
+          const int e = i * N + j, s = i * L::LD + j, t = j * L::LD + i;
+          g2[p * per + e] = 0.5 * (gx2[s] + gx2[t]);
+          g2[p * per + N * N + e] = 0.5 * (gy2[s] + gy2[t]);
+          g1[p * per + e] = -0.5 * (gx2[s] + gx2[t]);
+          g1[p * per + N * N + e] = 0.5 * (gy1[s] + gy1[t]);
         }
     }
   }
@@ -104,10 +125,14 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
     }
     return 1;
   }
-  if (variant == 2) {
+  if (variant == 2 || variant == 3) {
     if (kind != kUpper) return 1;
     switch (n) {
-#define CASE(K) case K: run_coop<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
+#define CASE(K)                                                                                  \
+  case K:                                                                                        \
+    if (variant == 2) run_coop<K, false>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); \
+    else run_coop<K, true>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status);              \
+    return 0;
       CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     }

@@ -34,23 +34,28 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.sympa_version() == 1
+    assert lib.sympa_version() == 2
     assert lib.sympa_error_string(0) == b"ok"
     assert lib.sympa_error_string(2).startswith(b"unsupported")
     # 2 operands * pairs * (2 n n) doubles * 8 bytes
     assert lib.sympa_workspace_bytes(0, 4, 1000) == 2 * 1000 * 32 * 8
     assert lib.sympa_workspace_bytes(2, 3, 10) == 2 * 10 * 9 * 8
     assert lib.sympa_workspace_bytes(0, 11, 10) == -1
+    # scratch: only upper n > 4 and batches worth splitting; five n x n planes + n per pair of a chunk, + (1 + n) per pair
+    assert lib.sympa_scratch_bytes(0, 4, 1 << 20) == 0
+    assert lib.sympa_scratch_bytes(1, 10, 1 << 20) == 0
+    assert lib.sympa_scratch_bytes(0, 10, 100) == 0
+    assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 32768 * 510 * 8 + (1 << 20) * 11 * 8
 
 
 def test_argument_errors_are_synchronous(lib):
     P = ctypes.c_void_p
     # unsupported n, and neither / both operand forms
-    assert lib.sympa_dist_forward(0, 64, 0, 1, P(8), P(8), None, 0, None, None, P(8), None, None, None, None) == 2
-    assert lib.sympa_dist_forward(0, 2, 0, 1, None, None, None, 0, None, None, P(8), None, None, None, None) == 1
-    assert lib.sympa_dist_forward(0, 2, 0, 1, P(8), P(8), P(8), 4, P(8), None, P(8), None, None, None, None) == 1
-    assert lib.sympa_dist_forward(0, 2, 4, 1, P(8), P(8), None, 0, None, None, P(8), None, None, None, None) == 1  # wsum without weights
-    assert lib.sympa_dist_forward(0, 2, 0, 0, P(8), P(8), None, 0, None, None, P(8), None, None, None, None) == 0  # empty batch
+    assert lib.sympa_dist_forward(0, 64, 0, 1, P(8), P(8), None, 0, None, None, P(8), None, None, None, 0, None, None) == 2
+    assert lib.sympa_dist_forward(0, 2, 0, 1, None, None, None, 0, None, None, P(8), None, None, None, 0, None, None) == 1
+    assert lib.sympa_dist_forward(0, 2, 0, 1, P(8), P(8), P(8), 4, P(8), None, P(8), None, None, None, 0, None, None) == 1
+    assert lib.sympa_dist_forward(0, 2, 4, 1, P(8), P(8), None, 0, None, None, P(8), None, None, None, 0, None, None) == 1  # wsum without weights
+    assert lib.sympa_dist_forward(0, 2, 0, 0, P(8), P(8), None, 0, None, None, P(8), None, None, None, 0, None, None) == 0  # empty batch
 
 
 def test_ops_refuse_cpu_tensors():

@@ -217,3 +217,58 @@ def test_full_size_properties(sb, kind, n):
     total = z1.grad.sum(0) + z2.grad.sum(0)
     torch.testing.assert_close(t.grad.sum(0), total, rtol=1e-8, atol=1e-8)
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("n", [5, 6, 10])
+@pytest.mark.parametrize("metric", ["riem", "wsum"])
+def test_split_path_equals_single_kernel_path(sb, n, metric):
+    """upper, n > 4: the three-kernel path (state parked in scratch; used when the batch is large enough
+    and scratch is given) must reproduce the single-kernel path bit for bit - forward, saved unit
+    gradients and the fused distortion step."""
+    from sympa_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(21 + n)
+    rows, b = 500, 5000       # > the 2048-pair threshold, not a multiple of the chunk or warp sizes
+    table = so.upper_spread(rows, n, generator=g, scale=0.3).cuda()
+    src = torch.randint(0, rows, (b,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    gd = torch.randint(1, 20, (b,), generator=g).double().cuda()
+    w = torch.linspace(-0.2, 1.1, n, dtype=torch.float64).cuda() if metric == "wsum" else None
+    assert lib.sympa_scratch_bytes(0, n, b) > 0
+    stream = torch.cuda.current_stream().cuda_stream
+    status = sb.ops.status_word(table.device)
+
+    def fwd(use_scratch):
+        dist = torch.empty(b, dtype=torch.float64, device="cuda")
+        vvd = torch.empty(b, n, dtype=torch.float64, device="cuda")
+        saved = torch.empty(lib.sympa_workspace_bytes(0, n, b) // 8, dtype=torch.float64, device="cuda")
+        scratch, nbytes = sb.ops.scratch_for("upper", n, b, table.device) if use_scratch else (None, 0)
+        _lib.check(lib.sympa_dist_forward(0, n, _lib.METRIC[metric], b, None, None, table.data_ptr(), rows,
+                                          idx.data_ptr(), None if w is None else w.data_ptr(), dist.data_ptr(),
+                                          vvd.data_ptr(), saved.data_ptr(),
+                                          None if scratch is None else scratch.data_ptr(), nbytes,
+                                          status.data_ptr(), stream))
+        return dist, vvd, saved
+
+    d0, v0, s0 = fwd(False)
+    d1, v1, s1 = fwd(True)
+    assert torch.equal(d0, d1) and torch.equal(v0, v1) and torch.equal(s0, s1)
+
+    def step(use_scratch):
+        gt = torch.zeros_like(table)
+        gs = torch.zeros(1, dtype=torch.float64, device="cuda")
+        gw = torch.zeros(n, dtype=torch.float64, device="cuda")
+        loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        scratch, nbytes = sb.ops.scratch_for("upper", n, b, table.device) if use_scratch else (None, 0)
+        _lib.check(lib.sympa_distortion_step(0, n, _lib.METRIC[metric], b, table.data_ptr(), rows, idx.data_ptr(),
+                                             gd.data_ptr(), 1.3, None if w is None else w.data_ptr(), gt.data_ptr(),
+                                             gw.data_ptr() if w is not None else None, gs.data_ptr(), loss.data_ptr(),
+                                             None, None if scratch is None else scratch.data_ptr(), nbytes,
+                                             status.data_ptr(), stream))
+        return gt, gs, gw, loss
+
+    a, b_ = step(False), step(True)
+    for x, y in zip(a, b_):
+        torch.testing.assert_close(x, y, rtol=1e-12, atol=1e-12)   # atomics: order differs, values do not
+    sb.ops.check_status()
