@@ -61,9 +61,16 @@ int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs);
 /* bytes of optional `scratch` (device memory, contents irrelevant, may be reused by the next call on
  * the same stream) that lets sympa_dist_forward / sympa_distortion_step run the larger matrix sizes
  * (upper half space, n > 4) as three kernels with the per-pair state parked in scratch instead of
- * shared memory (~2x faster there).  0 when the configuration does not use scratch.  Passing
- * scratch == NULL (or fewer bytes) is always valid: the single-kernel path is used. */
+ * shared memory.  0 when the configuration does not use scratch (always, unless the split path is
+ * switched on with sympa_set_option).  Passing scratch == NULL (or fewer bytes) is always valid:
+ * the single-kernel path is used. */
 int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
+
+/* process-wide tuning switches (host side only).  SYMPA_OPT_SPLIT_PATH: 0 (default) = larger matrix
+ * sizes run as ONE cooperative kernel; 1 = three kernels through `scratch` (sympa_scratch_bytes then
+ * reports a non-zero size).  Results are bit-identical either way. */
+#define SYMPA_OPT_SPLIT_PATH 1
+int sympa_set_option(int option, int value);
 
 /* Forward of manifold.dist (siegel_manifold.py:41-72, bounded_domain.py:27-39, geoopt spd dist).
  * Operands come either materialised (z1, z2: (num_pairs, point)) or as a fused gather

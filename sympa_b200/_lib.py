@@ -4,11 +4,12 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsympa_b200.so")
+LIB_PATH = os.environ.get("SYMPA_B200_LIB") or os.path.join(_PKG, "libsympa_b200.so")
 
 KIND = {"upper": 0, "bounded": 1, "spd": 2}
 METRIC = {"riem": 0, "fone": 1, "finf": 2, "fmin": 3, "wsum": 4}
 MAX_N = 10
+OPT_SPLIT_PATH = 1
 
 STATUS_BITS = {
     1: "a point is outside the manifold (Cholesky pivot <= 0)",
@@ -24,6 +25,7 @@ EXPORTS = (
     "sympa_last_cuda_error",
     "sympa_workspace_bytes",
     "sympa_scratch_bytes",
+    "sympa_set_option",
     "sympa_dist_forward",
     "sympa_dist_backward",
     "sympa_distortion_step",
@@ -52,6 +54,8 @@ def load():
     lib.sympa_last_cuda_error.restype = ctypes.c_char_p
     lib.sympa_workspace_bytes.restype = L
     lib.sympa_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_set_option.restype = I
+    lib.sympa_set_option.argtypes = [I, I]
     lib.sympa_scratch_bytes.restype = L
     lib.sympa_scratch_bytes.argtypes = [I, I, L]
     lib.sympa_dist_forward.restype = I

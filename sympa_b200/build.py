@@ -17,14 +17,16 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
-LIB_PATH = os.path.join(PKG_DIR, "libsympa_b200.so")
+LIB_PATH = os.environ.get("SYMPA_B200_LIB") or os.path.join(PKG_DIR, "libsympa_b200.so")
 MAX_N = 10
+
+EXTRA_FLAGS = os.environ.get("SYMPA_NVCC_EXTRA", "").split()
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + EXTRA_FLAGS
 
 
 def _nvcc():

@@ -137,11 +137,22 @@ template <int N, class Ex>
 SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, double* flag) {
   constexpr int G = Layout<N>::G;
   constexpr int LD = Layout<N>::LD;
+  // The k-loops below run over a fixed, fully unrolled range with a predicate instead of a runtime
+  // trip count: all the shared-memory loads of a dot product are then issued back to back and only
+  // the FMA chain stays serial (these stages are latency-bound, one warp per scheduler).
 #pragma unroll 1
   for (int j = 0; j < N; ++j) {
     SY_STAGE_BEGIN(ex)
-    double d = a[j * LD + j];
-    for (int k = 0; k < j; ++k) d -= l[j * LD + k] * l[j * LD + k];
+    double lj[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) lj[k] = (k < j) ? l[j * LD + k] : 0.0;
+    double d0 = a[j * LD + j], d1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+      d0 -= lj[k] * lj[k];
+      if (k + 1 < N) d1 -= lj[k + 1] * lj[k + 1];
+    }
+    const double d = d0 + d1;
     const double r = sy_rsqrt(d);
     for (int i = j + g; i < N; i += G) {
       if (i == j) {
@@ -149,22 +160,46 @@ SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, 
         rd[j] = r;
         if (!(d > 0.0)) *flag = 1.0;
       } else {
-        double s = a[i * LD + j];
-        for (int k = 0; k < j; ++k) s -= l[i * LD + k] * l[j * LD + k];
-        l[i * LD + j] = s * r;
+        double lik[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) lik[k] = (k < j) ? l[i * LD + k] : 0.0;
+        double s0 = a[i * LD + j], s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+          s0 -= lik[k] * lj[k];
+          if (k + 1 < N) s1 -= lik[k + 1] * lj[k + 1];
+        }
+        l[i * LD + j] = (s0 + s1) * r;
       }
     }
     SY_STAGE_END(ex)
   }
+  // inverse of the triangular factor: lane g solves for columns g and g + G, both at once
   SY_STAGE_BEGIN(ex)
-  for (int c = g; c < N; c += G) {
-    for (int i = 0; i < c; ++i) li[i * LD + c] = 0.0;
-    li[c * LD + c] = rd[c];
-    for (int i = c + 1; i < N; ++i) {
-      double s = 0.0;
-      for (int k = c; k < i; ++k) s += l[i * LD + k] * li[k * LD + c];
-      li[i * LD + c] = -s * rd[i];
+  const int c0 = g, c1 = g + G;
+  const bool two = c1 < N;
+  double x0[N], x1[N];  // the two columns of li being built (entries above the diagonal are zero)
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double li_row[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) li_row[k] = (k < i) ? l[i * LD + k] : 0.0;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (k < i) {
+        s0 += li_row[k] * x0[k];
+        s1 += li_row[k] * x1[k];
+      }
     }
+    const double r = rd[i];
+    x0[i] = (i == c0) ? r : ((i > c0) ? -s0 * r : 0.0);
+    x1[i] = (two && i == c1) ? r : ((two && i > c1) ? -s1 * r : 0.0);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    li[i * LD + c0] = x0[i];
+    if (two) li[i * LD + c1] = x1[i];
   }
   SY_STAGE_END(ex)
 }
@@ -611,10 +646,14 @@ SY_HD void upper_backward(Ex& ex, double* sm, const double* p1, const double* p2
   for (int e = g; e < NN; e += G) {
     const int i = e / N, j = e - i * N;
     if (i >= j) {
-      double a = 0.0;
-      for (int k = 0; k <= j; ++k) a += a0[i * LD + k] * li[j * LD + k];
-      a4[i * LD + j] = 0.5 * a;
-      a4[j * LD + i] = 0.5 * a;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; k += 2) {
+        s0 += (k <= j) ? a0[i * LD + k] * li[j * LD + k] : 0.0;
+        if (k + 1 < N) s1 += (k + 1 <= j) ? a0[i * LD + k + 1] * li[j * LD + k + 1] : 0.0;
+      }
+      a4[i * LD + j] = 0.5 * (s0 + s1);
+      a4[j * LD + i] = 0.5 * (s0 + s1);
     }
   }
   SY_STAGE_END(ex)

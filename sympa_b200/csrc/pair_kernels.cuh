@@ -47,6 +47,11 @@ int grid_for(int64_t work_items, int threads, int waves_cap);
 #ifdef SYMPA_PAIR_KERNELS_IMPL
 
 constexpr int kThreads = 128;
+// minimum resident CTAs per SM asked of ptxas for the register-resident sizes n = 3, 4 (caps the
+// registers per thread: 2 -> 255, 3 -> 168, 4 -> 128); tuned on the B200, see DESIGN.md
+#ifndef SY_REG_MIN_BLOCKS
+#define SY_REG_MIN_BLOCKS 2
+#endif
 
 // namespace switch: reg = unrolled / registers (N <= SY_REG_MAX_N), loc = rolled / local memory
 template <bool REG>
@@ -132,7 +137,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int N, int KIND, int MODE>
-__global__ void __launch_bounds__(kThreads) pair_kernel(const PairArgs a) {
+__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_REG_MIN_BLOCKS : 1) pair_kernel(const PairArgs a) {
   constexpr bool REG = N <= SY_REG_MAX_N;
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;

@@ -165,9 +165,21 @@ int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs) {
 static const int64_t kSplitChunkPairs = 32768;  // scratch per chunk stays L2-resident (n = 10: 134 MB .. n = 5: 35 MB)
 static const int64_t kSplitMinPairs = 2048;     // below this the single-kernel path is used
 
-static bool uses_scratch(int kind, int n) { return kind == SYMPA_KIND_UPPER && n > SY_REG_MAX_N; }
+// The three-kernel path is measured SLOWER than the single cooperative kernel in round 1 (its
+// prologue / backward kernels are latency-bound at the same occupancy); it stays selectable for
+// experiments and for its parity test: sympa_set_option(SYMPA_OPT_SPLIT_PATH, 1).
+static int g_split_enabled = 0;
+static bool uses_scratch(int kind, int n) { return g_split_enabled && kind == SYMPA_KIND_UPPER && n > SY_REG_MAX_N; }
 static int64_t scratch_per_pair_bytes(int n) { return (int64_t)(5 * n * n + n) * (int64_t)sizeof(double); }
 static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs * (int64_t)(1 + n) * (int64_t)sizeof(double); }
+
+int sympa_set_option(int option, int value) {
+  if (option == SYMPA_OPT_SPLIT_PATH) {
+    g_split_enabled = value != 0;
+    return SYMPA_OK;
+  }
+  return SYMPA_ERR_BAD_ARG;
+}
 
 int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs) {
   if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N || num_pairs < 0) return -1;

@@ -42,10 +42,16 @@ def test_host_only_entry_points(lib):
     assert lib.sympa_workspace_bytes(2, 3, 10) == 2 * 10 * 9 * 8
     assert lib.sympa_workspace_bytes(0, 11, 10) == -1
     # scratch: only upper n > 4 and batches worth splitting; five n x n planes + n per pair of a chunk, + (1 + n) per pair
-    assert lib.sympa_scratch_bytes(0, 4, 1 << 20) == 0
-    assert lib.sympa_scratch_bytes(1, 10, 1 << 20) == 0
-    assert lib.sympa_scratch_bytes(0, 10, 100) == 0
-    assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 32768 * 510 * 8 + (1 << 20) * 11 * 8
+    assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 0        # split path is off by default
+    assert lib.sympa_set_option(1, 1) == 0
+    try:
+        assert lib.sympa_scratch_bytes(0, 4, 1 << 20) == 0
+        assert lib.sympa_scratch_bytes(1, 10, 1 << 20) == 0
+        assert lib.sympa_scratch_bytes(0, 10, 100) == 0
+        assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 32768 * 510 * 8 + (1 << 20) * 11 * 8
+    finally:
+        assert lib.sympa_set_option(1, 0) == 0
+    assert lib.sympa_set_option(99, 0) == 1
 
 
 def test_argument_errors_are_synchronous(lib):

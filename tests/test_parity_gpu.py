@@ -235,7 +235,6 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
     idx = torch.stack((src, dst), 1).cuda()
     gd = torch.randint(1, 20, (b,), generator=g).double().cuda()
     w = torch.linspace(-0.2, 1.1, n, dtype=torch.float64).cuda() if metric == "wsum" else None
-    assert lib.sympa_scratch_bytes(0, n, b) > 0
     stream = torch.cuda.current_stream().cuda_stream
     status = sb.ops.status_word(table.device)
 
@@ -251,10 +250,6 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
                                           status.data_ptr(), stream))
         return dist, vvd, saved
 
-    d0, v0, s0 = fwd(False)
-    d1, v1, s1 = fwd(True)
-    assert torch.equal(d0, d1) and torch.equal(v0, v1) and torch.equal(s0, s1)
-
     def step(use_scratch):
         gt = torch.zeros_like(table)
         gs = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -268,7 +263,17 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
                                              status.data_ptr(), stream))
         return gt, gs, gw, loss
 
-    a, b_ = step(False), step(True)
+    d0, v0, s0 = fwd(False)
+    a = step(False)
+    assert lib.sympa_set_option(_lib.OPT_SPLIT_PATH, 1) == 0
+    try:
+        assert lib.sympa_scratch_bytes(0, n, b) > 0
+        d1, v1, s1 = fwd(True)
+        b_ = step(True)
+    finally:
+        lib.sympa_set_option(_lib.OPT_SPLIT_PATH, 0)
+    assert torch.equal(d0, d1) and torch.equal(v0, v1) and torch.equal(s0, s1)
     for x, y in zip(a, b_):
         torch.testing.assert_close(x, y, rtol=1e-12, atol=1e-12)   # atomics: order differs, values do not
     sb.ops.check_status()
+
