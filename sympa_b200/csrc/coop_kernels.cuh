@@ -26,14 +26,76 @@ struct CoopCfg {
   static constexpr int kSmemBytes = PW * L::kDoubles * (int)sizeof(double);
 };
 
+// writes the unit gradients (MODE fwd+save) or the scaled scatter-add (MODE step) from the results the
+// pair mathematics left in shared memory (symmetrised here)
+template <int N, int KIND, int MODE>
+__device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* sm, int g, int64_t p, int64_t i1,
+                                               int64_t i2, double dist, double* loss_acc, double* gscale_acc) {
+  typedef coop::Layout<N> L;
+  typedef coop::SpdLayout<N> S;
+  constexpr int G = L::G;
+  constexpr int NN = N * N;
+  constexpr int PER = (KIND == kSpd ? 1 : 2) * NN;
+  constexpr int LD = L::LD;
+  // upper: (re1, im1, re2, im2) = (-GX2, GY1, GX2, GY2);  spd: (re1, re2) = (GX, GY)
+  const double* r1 = sm + (KIND == kSpd ? S::SPD_GX : L::GX2);
+  const double* r2 = sm + (KIND == kSpd ? S::SPD_GY : L::GX2);
+  const double s1 = (KIND == kSpd) ? 1.0 : -1.0;
+  const double* m1 = sm + L::GY1;
+  const double* m2 = sm + L::GY2;
+  double scale = 1.0;
+  double* o1;
+  double* o2;
+  if (MODE == kModeFwdSave) {
+    o1 = a.gz1 + p * PER;
+    o2 = a.gz2 + p * PER;
+  } else {  // fused distortion step: L_p = |(s d / g)^2 - 1|  (losses.py:16-19, model.py:30)
+    const double gd = __ldg(a.graph_dist + p);
+    const double r = a.scale * dist / gd;
+    const double er = r * r - 1.0;
+    const double sg = er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0);
+    const double dl_dr = sg * 2.0 * r;
+    scale = dl_dr * a.scale / gd;
+    if (g == 0) {
+      *loss_acc += fabs(er);
+      *gscale_acc += dl_dr * dist / gd;
+    }
+    o1 = a.grad_table + i1 * PER;
+    o2 = a.grad_table + i2 * PER;
+  }
+  for (int e = g; e < NN; e += G) {
+    const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+    const double v1 = scale * s1 * 0.5 * (r1[s] + r1[t]);
+    const double v2 = scale * 0.5 * (r2[s] + r2[t]);
+    if (MODE == kModeFwdSave) {
+      o1[e] = v1;
+      o2[e] = v2;
+    } else {
+      atomicAdd(o1 + e, v1);
+      atomicAdd(o2 + e, v2);
+    }
+    if (KIND != kSpd) {
+      const double w1 = scale * 0.5 * (m1[s] + m1[t]);
+      const double w2 = scale * 0.5 * (m2[s] + m2[t]);
+      if (MODE == kModeFwdSave) {
+        o1[NN + e] = w1;
+        o2[NN + e] = w2;
+      } else {
+        atomicAdd(o1 + NN + e, w1);
+        atomicAdd(o2 + NN + e, w2);
+      }
+    }
+  }
+}
+
 template <int N, int KIND, int MODE>
 __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
-  static_assert(KIND == kUpper, "cooperative kernel: upper half space only");
+  static_assert(KIND == kUpper || KIND == kSpd, "cooperative kernel: upper half space and spd");
   typedef coop::Layout<N> L;
   constexpr int G = CoopCfg<N>::G;
   constexpr int PW = CoopCfg<N>::PW;
   constexpr int NN = N * N;
-  constexpr int PER = 2 * NN;
+  constexpr int PER = (KIND == kSpd ? 1 : 2) * NN;
   constexpr bool GRAD = MODE != kModeFwd;
   extern __shared__ double smem[];
   const int lane = threadIdx.x;
@@ -67,7 +129,10 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
       }
     }
     WarpExec ex{g, active};
-    coop::upper_pair<N, GRAD>(ex, sm, p1, p2, a.metric, a.wsum_w);
+    if (KIND == kSpd)
+      coop::spd_pair<N, GRAD>(ex, sm, p1, p2);
+    else
+      coop::upper_pair<N, GRAD>(ex, sm, p1, p2, a.metric, a.wsum_w);
     if (active) {
       const double dist = sm[L::DIST];
       if (g == 0) {
@@ -78,47 +143,15 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
         for (int k = g; k < N; k += G) a.vvd_out[p * N + k] = sm[L::VS + k];
       }
       if (GRAD) {
-        const double* gx2 = sm + L::GX2;
-        const double* gy2 = sm + L::GY2;
-        const double* gy1 = sm + L::GY1;
-        constexpr int LD = L::LD;
-        if (MODE == kModeFwdSave) {
-          double* o1 = a.gz1 + p * PER;
-          double* o2 = a.gz2 + p * PER;
-          for (int e = g; e < NN; e += G) {
-            const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
-            const double x2 = 0.5 * (gx2[s] + gx2[t]);
-            o2[e] = x2;
-            o1[e] = -x2;
-            o2[NN + e] = 0.5 * (gy2[s] + gy2[t]);
-            o1[NN + e] = 0.5 * (gy1[s] + gy1[t]);
-          }
-        } else {  // fused distortion step
+        if (MODE == kModeStep && KIND != kSpd && a.grad_wsum_w != nullptr && a.metric == kWsum) {
           const double gd = __ldg(a.graph_dist + p);
           const double r = a.scale * dist / gd;
           const double er = r * r - 1.0;
-          const double sg = er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0);
-          const double dl_dr = sg * 2.0 * r;
-          const double dl_dd = dl_dr * a.scale / gd;
-          if (g == 0) {
-            loss_acc += fabs(er);
-            gscale_acc += dl_dr * dist / gd;
-          }
-          if (a.grad_wsum_w != nullptr && a.metric == kWsum) {
-            for (int k = g; k < N; k += G)
-              if (a.wsum_w[k] > 0.0) atomicAdd(a.grad_wsum_w + k, dl_dd * sm[L::VS + k]);
-          }
-          double* o1 = a.grad_table + i1 * PER;
-          double* o2 = a.grad_table + i2 * PER;
-          for (int e = g; e < NN; e += G) {
-            const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
-            const double x2 = dl_dd * 0.5 * (gx2[s] + gx2[t]);
-            atomicAdd(o2 + e, x2);
-            atomicAdd(o1 + e, -x2);
-            atomicAdd(o2 + NN + e, dl_dd * 0.5 * (gy2[s] + gy2[t]));
-            atomicAdd(o1 + NN + e, dl_dd * 0.5 * (gy1[s] + gy1[t]));
-          }
+          const double dl_dd = (er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0)) * 2.0 * r * a.scale / gd;
+          for (int k = g; k < N; k += G)
+            if (a.wsum_w[k] > 0.0) atomicAdd(a.grad_wsum_w + k, dl_dd * sm[L::VS + k]);
         }
+        emit_gradients<N, KIND, MODE>(a, sm, g, p, i1, i2, dist, &loss_acc, &gscale_acc);
       }
     }
     __syncwarp();
@@ -233,54 +266,6 @@ __global__ void __launch_bounds__(32) coop_spectrum_kernel(const PairArgs a, con
   if (st != 0 && lane == 0 && a.status != nullptr) atomicOr(a.status, st);
 }
 
-// writes the unit gradients (MODE fwd+save) or the scaled scatter-add (MODE step) from the results
-// upper_backward left in shared memory
-template <int N, int MODE>
-__device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* sm, int g, int64_t p, int64_t i1,
-                                               int64_t i2, double dist, double* loss_acc, double* gscale_acc) {
-  typedef coop::Layout<N> L;
-  constexpr int G = L::G;
-  constexpr int NN = N * N;
-  constexpr int PER = 2 * NN;
-  constexpr int LD = L::LD;
-  const double* gx2 = sm + L::GX2;
-  const double* gy2 = sm + L::GY2;
-  const double* gy1 = sm + L::GY1;
-  if (MODE == kModeFwdSave) {
-    double* o1 = a.gz1 + p * PER;
-    double* o2 = a.gz2 + p * PER;
-    for (int e = g; e < NN; e += G) {
-      const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
-      const double x2 = 0.5 * (gx2[s] + gx2[t]);
-      o2[e] = x2;
-      o1[e] = -x2;
-      o2[NN + e] = 0.5 * (gy2[s] + gy2[t]);
-      o1[NN + e] = 0.5 * (gy1[s] + gy1[t]);
-    }
-  } else {  // fused distortion step: L_p = |(s d / g)^2 - 1|  (losses.py:16-19, model.py:30)
-    const double gd = __ldg(a.graph_dist + p);
-    const double r = a.scale * dist / gd;
-    const double er = r * r - 1.0;
-    const double sg = er > 0.0 ? 1.0 : (er < 0.0 ? -1.0 : 0.0);
-    const double dl_dr = sg * 2.0 * r;
-    const double dl_dd = dl_dr * a.scale / gd;
-    if (g == 0) {
-      *loss_acc += fabs(er);
-      *gscale_acc += dl_dr * dist / gd;
-    }
-    double* o1 = a.grad_table + i1 * PER;
-    double* o2 = a.grad_table + i2 * PER;
-    for (int e = g; e < NN; e += G) {
-      const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
-      const double x2 = dl_dd * 0.5 * (gx2[s] + gx2[t]);
-      atomicAdd(o2 + e, x2);
-      atomicAdd(o1 + e, -x2);
-      atomicAdd(o2 + NN + e, dl_dd * 0.5 * (gy2[s] + gy2[t]));
-      atomicAdd(o1 + NN + e, dl_dd * 0.5 * (gy1[s] + gy1[t]));
-    }
-  }
-}
-
 template <int N, int MODE>
 __global__ void __launch_bounds__(32) coop_backward_kernel(const PairArgs a, const ChunkArgs c) {
   typedef coop::Layout<N> L;
@@ -313,7 +298,7 @@ __global__ void __launch_bounds__(32) coop_backward_kernel(const PairArgs a, con
         for (int k = g; k < N; k += G)
           if (a.wsum_w[k] > 0.0) atomicAdd(a.grad_wsum_w + k, dl_dd * a.vvd_out[p * N + k]);
       }
-      emit_gradients<N, MODE>(a, sm, g, p, i1, i2, dist, &loss_acc, &gscale_acc);
+      emit_gradients<N, kUpper, MODE>(a, sm, g, p, i1, i2, dist, &loss_acc, &gscale_acc);
     }
     __syncwarp();
   }

@@ -134,7 +134,8 @@ SY_HD void mm_stage(const double* a, const double* b, double* c, int g, double s
 // Inverse Cholesky factor, cooperative: a (full symmetric, lower part used) -> li (full, upper part
 // zeroed); l = scratch buffer, rd = n doubles.  N + 1 stages.
 template <int N, class Ex>
-SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, double* flag) {
+SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, double* flag,
+                    bool keep_l = false) {  // keep_l: leave a clean lower-triangular L in `l` (upper part zeroed)
   constexpr int G = Layout<N>::G;
   constexpr int LD = Layout<N>::LD;
   // The k-loops below run over a fixed, fully unrolled range with a predicate instead of a runtime
@@ -201,6 +202,11 @@ SY_HD void chol_inv(Ex& ex, const double* a, double* l, double* li, double* rd, 
     li[i * LD + c0] = x0[i];
     if (two) li[i * LD + c1] = x1[i];
   }
+  if (keep_l) {
+    for (int i = 0; i < c0; ++i) l[i * LD + c0] = 0.0;
+    if (two)
+      for (int i = 0; i < c1; ++i) l[i * LD + c1] = 0.0;
+  }
   SY_STAGE_END(ex)
 }
 
@@ -243,23 +249,13 @@ SY_HD void inv_spd_real(Ex& ex, double* e, const double* f, double* u, double* v
 template <int N>
 SY_HD void tournament(int r, int k, int* p, int* q) {
   constexpr int NP = Layout<N>::NP;
-  int a, b;
-  if (k == 0) {
-    a = NP - 1;
-    b = r;
-  } else {
-    a = r + k;
-    a = a >= NP - 1 ? a - (NP - 1) : a;
-    b = r - k;
-    b = b < 0 ? b + (NP - 1) : b;
-  }
-  *p = a < b ? a : b;
-  *q = a < b ? b : a;
+  (void)NP;
+  loc::tournament_pair<N>(r, k, p, q);
 }
 
 // One-sided Jacobi on the column-major complex matrix (gr, gi) in shared memory, column stride LD
 // (no V).  `conv` holds 2 * G not-converged flags, double-buffered by sweep parity.
-template <int N, class Ex>
+template <int N, bool IS_REAL, class Ex>
 SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* conv) {
   constexpr int NP = Layout<N>::NP;
   constexpr int G = Layout<N>::G;
@@ -279,9 +275,9 @@ SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* conv) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           pr[i] = gr[p * LD + i];
-          pi[i] = gi[p * LD + i];
           qr[i] = gr[q * LD + i];
-          qi[i] = gi[q * LD + i];
+          pi[i] = IS_REAL ? 0.0 : gi[p * LD + i];
+          qi[i] = IS_REAL ? 0.0 : gi[q * LD + i];
         }
         // two partial sums per quantity: shorter dependency chains
         double al0 = 0.0, be0 = 0.0, cr0 = 0.0, ci0 = 0.0, al1 = 0.0, be1 = 0.0, cr1 = 0.0, ci1 = 0.0;
@@ -297,27 +293,20 @@ SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* conv) {
           ci1 += pi[i] * qr[i];
         }
         const double al = al0 + al1, be = be0 + be1, cr = cr0 + cr1, ci = ci0 - ci1;
-        const double g2 = cr * cr + ci * ci;
-        const double ab = al * be;
-        if (g2 > reg::kSkipRatio2 * ab) {
-          notconv = (g2 > reg::kStopRatio2 * ab) ? 1.0 : 0.0;
-          const double dl = 0.5 * (be - al);
-          const double h = dl * dl + g2;
-          const double den = fabs(dl) + h * sy_rsqrt(h);
-          const double rden = sy_rsqrt(den);
-          double inv = rden * rden;
-          inv = dl < 0.0 ? -inv : inv;
-          const double tr_ = cr * inv, ti_ = ci * inv;
-          const double c = sy_rsqrt(1.0 + tr_ * tr_ + ti_ * ti_);
-          const double sr = c * tr_, si = c * ti_;
+        bool more = false;
+        double c, sr, si;
+        if (loc::jacobi_rotation(al, be, cr, ci, &c, &sr, &si, &more)) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             gr[p * LD + i] = c * pr[i] - (sr * qr[i] + si * qi[i]);
-            gi[p * LD + i] = c * pi[i] - (sr * qi[i] - si * qr[i]);
             gr[q * LD + i] = c * qr[i] + (sr * pr[i] - si * pi[i]);
-            gi[q * LD + i] = c * qi[i] + (sr * pi[i] + si * pr[i]);
+            if (!IS_REAL) {
+              gi[p * LD + i] = c * pi[i] - (sr * qi[i] - si * qr[i]);
+              gi[q * LD + i] = c * qi[i] + (sr * pi[i] + si * pr[i]);
+            }
           }
         }
+        notconv = more ? 1.0 : 0.0;
       }
       wbuf[g] = (r == 0) ? notconv : (notconv > wbuf[g] ? notconv : wbuf[g]);
       SY_STAGE_END(ex)
@@ -483,7 +472,7 @@ SY_HD void spectrum(Ex& ex, double* sm, int metric, const double* wsum_w) {
   constexpr int LD = LT::LD;
   double* gr = sm + LT::GR;
   double* gi = sm + LT::GI;
-  const int sweeps = jacobi<N>(ex, gr, gi, sm + LT::WORST);
+  const int sweeps = jacobi<N, false>(ex, gr, gi, sm + LT::WORST);
   SY_STAGE_BEGIN(ex)
   for (int k = g; k < N; k += G) {
     double s0 = 0.0, s1 = 0.0;
@@ -759,6 +748,150 @@ SY_HD void upper_pair(Ex& ex, double* sm, const double* p1, const double* p2, in
   w_from_pq<N>(ex, sm + L::PBUF, sm + L::QBUF, L::LD, sm + L::GR, sm + L::GI);
   spectrum<N, L>(ex, sm, metric, wsum_w);
   if (GRAD) upper_backward<N>(ex, sm, p1, p2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPD (affine-invariant) distance, one pair, cooperative: dist^2 = sum log^2 lambda_i(X^-1 Y),
+// lambda = sigma^2 of Gm = Lx^-1 Ly (see spd_pair in pair_math_impl.inc).  p1 / p2 point at the
+// (n, n) rows.  Results: sm[DIST], sm[VS..], sm[FLAG]; GRAD: d dist / dX = sm[SPD_GX], d/dY = sm[SPD_GY].
+template <int N>
+struct SpdLayout : Layout<N> {
+  typedef Layout<N> B;
+  static constexpr int XI = B::LI, LY = B::A0, LYI = B::A1, GM = B::A2, GJ = B::A3, T0 = B::A4, T1 = B::A5;
+  static constexpr int SPD_GX = T0, SPD_GY = T1;
+};
+
+template <int N, bool GRAD, class Ex>
+SY_HD void spd_pair(Ex& ex, double* sm, const double* p1, const double* p2) {
+  typedef SpdLayout<N> L;
+  constexpr int G = L::G;
+  constexpr int NN = L::NN;
+  constexpr int LD = L::LD;
+  double* xi = sm + L::XI;
+  double* ly = sm + L::LY;
+  double* lyi = sm + L::LYI;
+  double* gm = sm + L::GM;
+  double* gj = sm + L::GJ;
+  double* t0 = sm + L::T0;
+  double* t1 = sm + L::T1;
+  double* rd = sm + L::RD;
+  double* flag = sm + L::FLAG;
+
+  SY_STAGE_BEGIN(ex)
+  if (g == 0) *flag = 0.0;
+  for (int e = g; e < NN; e += G) {
+    const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
+    t0[s] = 0.5 * (SY_LDG(p1 + e) + SY_LDG(p1 + et));
+    t1[s] = 0.5 * (SY_LDG(p2 + e) + SY_LDG(p2 + et));
+  }
+  SY_STAGE_END(ex)
+  chol_inv<N>(ex, t0, gj, xi, rd, flag);         // xi = chol(X)^-1
+  chol_inv<N>(ex, t1, ly, lyi, rd, flag, true);  // ly = chol(Y), lyi = its inverse
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, false, false>(xi, ly, gm, g, 1.0, 0.0);  // Gm = Lx^-1 Ly (lower triangular)
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  for (int e = g; e < NN; e += G) {
+    const int c = e / N, r = e - c * N;
+    gj[c * LD + r] = gm[r * LD + c];  // column-major copy for the Jacobi
+  }
+  SY_STAGE_END(ex)
+  const int sweeps = jacobi<N, true>(ex, gj, gj, sm + L::WORST);
+  SY_STAGE_BEGIN(ex)
+  for (int k = g; k < N; k += G) {
+    double s0 = 0.0;
+    for (int i = 0; i < N; ++i) s0 += gj[k * LD + i] * gj[k * LD + i];
+    const double sig = sqrt(s0);
+    sm[L::SIG + k] = sig;
+    sm[L::VK + k] = 2.0 * log(sig);
+  }
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  double ss = 0.0;
+  for (int k = 0; k < N; ++k) ss += sm[L::VK + k] * sm[L::VK + k];
+  const double dist = sqrt(ss);
+  const double inv = dist > 0.0 ? 1.0 / dist : 0.0;
+  for (int k = g; k < N; k += G) {
+    const double d = sm[L::SIG + k];
+    int r = 0;
+    for (int j = 0; j < N; ++j) {
+      const double o = sm[L::SIG + j];
+      r += (o < d || (o == d && j < k)) ? 1 : 0;
+    }
+    sm[L::VS + r] = sm[L::VK + k];
+    const double s2 = d * d;
+    sm[L::COEF + k] = sm[L::VK + k] * inv * 2.0 / (s2 * s2);  // (dL/dsigma_k) / sigma_k^3
+  }
+  if (g == 0) {
+    unsigned st = (*flag != 0.0) ? kStatusNotPD : 0u;
+    if (sweeps >= kMaxSweeps) st |= kStatusNoConverge;
+    if (!(dist == dist) || dist > 1e300) st |= kStatusNonFinite;
+    sm[L::DIST] = dist;
+    *flag = (double)st;
+  }
+  SY_STAGE_END(ex)
+  if (!GRAD) return;
+
+  // F = sum_k coef_k g_k g_k^T -> t0
+  SY_STAGE_BEGIN(ex)
+  const int j0 = g, j1 = g + G;
+  const bool two = j1 < N;
+  const int jj1 = two ? j1 : j0;
+  double f0[N], f1[N];
+  zero2<N>(f0, f1);
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    const double c = sm[L::COEF + k];
+    const double b0 = c * gj[k * LD + j0];
+    const double b1 = two ? c * gj[k * LD + jj1] : 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double a = gj[k * LD + i];
+      f0[i] += a * b0;
+      f1[i] += a * b1;
+    }
+  }
+  put_cols<N>(t0, j0, j1, f0, f1, 1.0, 0.0);
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, false, false>(t0, gm, t1, g, 1.0, 0.0);  // t1 = G_Gm = F Gm
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, true, false>(xi, t1, gj, g, 1.0, 0.0);   // gj = Lxi^T G_Gm   (lower part = G_Ly)
+  mm_stage<N, false, true>(t1, ly, t0, g, 1.0, 0.0);   // t0 = G_Gm Ly^T    (lower part = G_Lxi)
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, true, false>(ly, gj, t1, g, 1.0, 0.0);   // t1 = Ly^T G_Ly    (lower part used)
+  mm_stage<N, false, true>(t0, xi, gm, g, 1.0, 0.0);   // gm = G_Lxi Lxi^T  (lower part used)
+  SY_STAGE_END(ex)
+  // Phi = 0.5 tril(.) mirrored (in place: the upper triangle is written only by the owner of (i, j))
+  SY_STAGE_BEGIN(ex)
+  for (int e = g; e < NN; e += G) {
+    const int i = e / N, j = e - i * N;
+    if (i >= j) {
+      const double a = 0.5 * t1[i * LD + j], b = 0.5 * gm[i * LD + j];
+      t1[i * LD + j] = a;
+      t1[j * LD + i] = a;
+      gm[i * LD + j] = b;
+      gm[j * LD + i] = b;
+    }
+  }
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, false, false>(t1, lyi, gj, g, 1.0, 0.0);  // gj = Phi Lyi
+  mm_stage<N, false, false>(gm, xi, t0, g, 1.0, 0.0);   // t0 = K_s Lxi
+  SY_STAGE_END(ex)
+  SY_STAGE_BEGIN(ex)
+  mm_stage<N, true, false>(lyi, gj, t1, g, 1.0, 0.0);   // t1 = G_Y = Lyi^T Phi Lyi
+  mm_stage<N, true, false>(xi, t0, gm, g, -1.0, 0.0);   // gm = G_X = -Lxi^T K_s Lxi
+  SY_STAGE_END(ex)
+  // move G_X where the layout promises it (t0)
+  SY_STAGE_BEGIN(ex)
+  for (int e = g; e < NN; e += G) {
+    const int i = e / N, j = e - i * N;
+    t0[i * LD + j] = gm[i * LD + j];
+  }
+  SY_STAGE_END(ex)
 }
 
 }  // namespace coop

@@ -266,6 +266,8 @@ static int launch_any(const PairArgs& a, cudaStream_t s) {
   if constexpr (KIND == kUpper && (N > SY_REG_MAX_N)) {
     if (a.scratch != nullptr && a.scratch_pairs > 0) return launch_split<N, MODE>(a, a.scratch, a.scratch_pairs, s);
     return launch_coop<N, KIND, MODE>(a, s);
+  } else if constexpr (KIND == kSpd && (N > SY_REG_MAX_N)) {
+    return launch_coop<N, KIND, MODE>(a, s);
   } else {
     return launch_one<N, KIND, MODE>(a, s);
   }

@@ -47,7 +47,7 @@ def hostcheck():
     """tests/hostcheck: the per-pair CUDA templates compiled for the host with g++."""
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     lib = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    deps = [src] + glob.glob(os.path.join(ROOT, "sympa_b200", "csrc", "pair_math*"))
+    deps = [src] + glob.glob(os.path.join(ROOT, "sympa_b200", "csrc", "pair_math*")) + glob.glob(os.path.join(ROOT, "sympa_b200", "csrc", "coop_math*"))
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", lib, src])
     dll = ctypes.CDLL(lib)

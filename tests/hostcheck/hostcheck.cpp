@@ -67,6 +67,30 @@ static void run_coop(int kind, int metric, int64_t b, const double* z1, const do
                      double* dist, double* vvd, double* g1, double* g2, unsigned* status) {
   typedef coop::Layout<N> L;
   typedef coop::LayoutJ<N> LJ;
+  if (kind == kSpd) {
+    typedef coop::SpdLayout<N> S;
+    std::vector<double> sm(S::kDoubles);
+    coop::HostExec ex{S::G};
+    const int per = N * N;
+    for (int64_t p = 0; p < b; ++p) {
+      for (auto& x : sm) x = -7.0e300;
+      if (grad)
+        coop::spd_pair<N, true>(ex, sm.data(), z1 + p * per, z2 + p * per);
+      else
+        coop::spd_pair<N, false>(ex, sm.data(), z1 + p * per, z2 + p * per);
+      dist[p] = sm[S::DIST];
+      for (int k = 0; k < N; ++k) vvd[p * N + k] = sm[S::VS + k];
+      *status |= (unsigned)sm[S::FLAG];
+      if (grad)
+        for (int i = 0; i < N; ++i)
+          for (int j = 0; j < N; ++j) {
+            const int s = i * S::LD + j, t = j * S::LD + i;
+            g1[p * per + i * N + j] = 0.5 * (sm[S::SPD_GX + s] + sm[S::SPD_GX + t]);
+            g2[p * per + i * N + j] = 0.5 * (sm[S::SPD_GY + s] + sm[S::SPD_GY + t]);
+          }
+    }
+    return;
+  }
   const int per = 2 * N * N;
   std::vector<double> sm(L::kDoubles), smj(LJ::kDoubles);
   const int64_t cap = 3;  // scratch capacity in pairs; the slot rotates so that the indexing is exercised
@@ -126,7 +150,7 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
     return 1;
   }
   if (variant == 2 || variant == 3) {
-    if (kind != kUpper) return 1;
+    if (kind == kBounded) return 1;
     switch (n) {
 #define CASE(K)                                                                                  \
   case K:                                                                                        \

@@ -38,7 +38,7 @@ def test_spd_against_oracle(hostcheck, n):
     x, y = so.spd_spread(16, n, generator=g), so.spd_spread(16, n, generator=g)
     go = torch.rand(16, generator=g, dtype=torch.float64) + 0.5
     d, g1, g2, _ = so.dist_and_grads("spd", x, y, grad_out=go)
-    for variant in ((0, 1) if n <= 4 else (1,)):
+    for variant in ((0, 1, 2) if n <= 4 else (1, 2)):     # 2 = cooperative kernel templates
         dd, vv, h1, h2, st = hostcheck(variant, "spd", n, "riem", x.numpy(), y.numpy())
         assert st == 0
         np.testing.assert_allclose(dd, d.numpy(), rtol=1e-9)
