@@ -22,6 +22,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 import torch  # noqa: E402
 
@@ -297,6 +299,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
     }
+    if not args.no_extras:
+        out["also"] = extras(args, world, rank, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(kind, n, args.metric, budget_s=args.cpu_budget)
     if rank == 0:
@@ -304,6 +308,82 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def quick_pairs_per_s(kind, n, metric, pairs, rows, dev, world, steps=5):
+    """resident fwd+bwd pairs/s of another configuration (same step shape as the main measurement)."""
+    import torch.distributed as dist
+    from sympa_b200 import BoundedDomainManifold, MetricType, SymmetricPositiveDefinite, UpperHalfManifold
+    from sympa_b200 import distributed as sd
+    man = (SymmetricPositiveDefinite() if kind == "spd" else
+           {"upper": UpperHalfManifold, "bounded": BoundedDomainManifold}[kind](dims=n, metric=MetricType.from_str(metric))).to(dev)
+    table = make_table(kind, n, rows, dev, seed=2).requires_grad_(True)
+    idx, gd = make_pairs(rows, pairs, dev, seed=300)
+
+    def step():
+        table.grad = None
+        d = man.dist_from_table(table, idx)
+        distortion_loss(gd, d).backward()
+        if world > 1:
+            sd.allreduce_gradients([table.grad], average=True)
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return world * pairs * steps / (ms * 1e-3)
+
+
+def epoch_seconds(dev, world, rank, epochs=3):
+    """BASELINE config 1: grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2, batch 2048,
+    RiemannianSGD - seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept)."""
+    from types import SimpleNamespace
+    from sympa_b200.graphs import grid_triplets
+    from sympa_b200.model import Model
+    from sympa_b200.optim import RiemannianSGD
+    from sympa_b200.runner import train_epoch
+    torch.manual_seed(0)
+    idx, gd, nodes = grid_triplets(20, 2)
+    args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                           train_scale=False)
+    model = Model(args).to(dev)
+    opt = RiemannianSGD(model.parameters(), lr=1e-2 * world)
+    idx, gd = idx.to(dev), gd.to(dev)
+    train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for ep in range(1, epochs + 1):
+        loss = train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=ep)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / epochs, loss
+
+
+def extras(args, world, rank, dev):
+    """The other sizes BASELINE.json's metric names (n = 10) and its epoch-time leg, measured briefly."""
+    out = {}
+    try:
+        out["upper_n10_fmin_pairs_per_s"] = quick_pairs_per_s("upper", 10, "fmin", 1 << 18, 1 << 18, dev, world)
+        out["upper_n2_riem_pairs_per_s"] = quick_pairs_per_s("upper", 2, "riem", 1 << 22, 1 << 20, dev, world)
+        out["spd_n10_pairs_per_s"] = quick_pairs_per_s("spd", 10, "riem", 1 << 18, 1 << 18, dev, world)
+        out["bounded_n3_fone_pairs_per_s"] = quick_pairs_per_s("bounded", 3, "fone", 1 << 22, 1 << 20, dev, world)
+        sec, loss = epoch_seconds(dev, world, rank)
+        out["train_epoch_sec_config1_grid400_upper_riem_n2_b2048"] = sec
+        out["train_epoch_final_loss"] = loss
+    except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
+        out["error"] = repr(e)
+    return out
 
 
 def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
@@ -391,6 +471,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1 << 20)
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default by n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the n=10 / epoch-time side measurements")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -277,3 +277,44 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
         torch.testing.assert_close(x, y, rtol=1e-12, atol=1e-12)   # atomics: order differs, values do not
     sb.ops.check_status()
 
+
+
+@pytest.mark.parametrize("kind,metric,n", [("upper", "riem", 2), ("bounded", "fone", 3)])
+def test_train_epoch_matches_oracle_loop(sb, kind, metric, n):
+    """One epoch of the training loop (runner.py:90-122: forward, distortion loss, backward, clip,
+    RiemannianSGD) on a small grid graph against the same loop driven by the oracle on the CPU."""
+    from types import SimpleNamespace
+    from torch.nn.utils import clip_grad_norm_
+    from sympa_b200.graphs import grid_triplets
+    from sympa_b200.model import Model
+    from sympa_b200.optim import RiemannianSGD
+    from sympa_b200.runner import train_epoch
+
+    torch.manual_seed(0)
+    idx, gd, nodes = grid_triplets(5, 2)
+    args = SimpleNamespace(manifold=kind, metric=metric, dims=n, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                           train_scale=False)
+    model = Model(args)
+    table0 = model.embeddings.embeds.detach().clone()
+    model = model.cuda()
+    lr, bs = 1e-2, 64
+    opt = RiemannianSGD(model.parameters(), lr=lr)
+    mean_loss = train_epoch(model, opt, idx.cuda(), gd.cuda(), bs, max_grad_norm=50.0, shuffle=False)
+
+    table = table0.clone()
+    total, steps = 0.0, 0
+    for s in range(0, idx.shape[0], bs):
+        sel = slice(s, s + bs)
+        t = table.clone().requires_grad_(True)
+        d = so.dist(kind, t[idx[sel, 0]], t[idx[sel, 1]], metric)
+        loss = so.distortion_loss(gd[sel], d)
+        loss.backward()
+        g = 0.5 * (t.grad + t.grad.transpose(-1, -2))
+        holder = torch.nn.Parameter(torch.zeros_like(g))
+        holder.grad = g
+        clip_grad_norm_([holder], 50.0)
+        table = so.rsgd_step(kind, table, holder.grad, lr)
+        total += loss.item()
+        steps += 1
+    np.testing.assert_allclose(mean_loss, total / steps, rtol=1e-7)
+    torch.testing.assert_close(model.embeddings.embeds.detach().cpu(), table, rtol=1e-6, atol=1e-9)
