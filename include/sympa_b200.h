@@ -72,6 +72,12 @@ int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
 #define SYMPA_OPT_SPLIT_PATH 1
 int sympa_set_option(int option, int value);
 
+/* Diagnostic: launches a pure FP64 FMA kernel (8 independent chains per thread, 8 CTAs of 256 threads
+ * per SM, `iters` FMAs per chain) on `stream` and returns the number of floating-point operations it
+ * issues (-1 on error); time it with events to get the device's attainable FP64 rate, the roofline
+ * denominator bench.py reports for this FP64-pipe-bound path.  `out`: one device double (not written). */
+int64_t sympa_probe_fp64(int iters, double* out, void* stream);
+
 /* Forward of manifold.dist (siegel_manifold.py:41-72, bounded_domain.py:27-39, geoopt spd dist).
  * Operands come either materialised (z1, z2: (num_pairs, point)) or as a fused gather
  * (table + idx; replaces Embeddings.forward, sympa/embeddings.py:29-34).  Exactly one of the two

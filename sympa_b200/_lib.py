@@ -26,6 +26,7 @@ EXPORTS = (
     "sympa_workspace_bytes",
     "sympa_scratch_bytes",
     "sympa_set_option",
+    "sympa_probe_fp64",
     "sympa_dist_forward",
     "sympa_dist_backward",
     "sympa_distortion_step",
@@ -54,6 +55,8 @@ def load():
     lib.sympa_last_cuda_error.restype = ctypes.c_char_p
     lib.sympa_workspace_bytes.restype = L
     lib.sympa_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_probe_fp64.restype = L
+    lib.sympa_probe_fp64.argtypes = [I, P, P]
     lib.sympa_set_option.restype = I
     lib.sympa_set_option.argtypes = [I, I]
     lib.sympa_scratch_bytes.restype = L

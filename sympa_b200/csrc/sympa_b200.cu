@@ -84,6 +84,27 @@ __global__ void __launch_bounds__(256) wsum_grad_kernel(int64_t num_pairs, int n
   }
 }
 
+// FP64 FMA throughput probe (diagnostic: gives bench.py a MEASURED FP64 roofline denominator; the
+// driver's MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).  8 independent FMA chains/thread.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed, double* __restrict__ out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) out[0] = r;  // never true: keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------ host
 static thread_local char g_last_cuda_error[256] = "";
 
@@ -172,6 +193,14 @@ static int g_split_enabled = 0;
 static bool uses_scratch(int kind, int n) { return g_split_enabled && kind == SYMPA_KIND_UPPER && n > SY_REG_MAX_N; }
 static int64_t scratch_per_pair_bytes(int n) { return (int64_t)(5 * n * n + n) * (int64_t)sizeof(double); }
 static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs * (int64_t)(1 + n) * (int64_t)sizeof(double); }
+
+int64_t sympa_probe_fp64(int iters, double* out, void* stream) {
+  if (iters <= 0 || out == nullptr) return -1;
+  const int blocks = sm_count() * 8;
+  fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, out);
+  if (check_launch()) return -1;
+  return (int64_t)blocks * 256 * 8 * 2 * (int64_t)iters;  // floating-point operations issued
+}
 
 int sympa_set_option(int option, int value) {
   if (option == SYMPA_OPT_SPLIT_PATH) {

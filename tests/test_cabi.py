@@ -20,7 +20,7 @@ def lib():
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "sympa_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sympa_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(sympa_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_what_the_binding_lists():
