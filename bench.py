@@ -370,7 +370,7 @@ def quick_pairs_per_s(kind, n, metric, pairs, rows, dev, world, steps=5):
     return world * pairs * steps / (ms * 1e-3)
 
 
-def epoch_seconds(dev, world, rank, epochs=3):
+def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True):
     """BASELINE config 1: grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2, batch 2048,
     RiemannianSGD - seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept)."""
     from types import SimpleNamespace
@@ -383,13 +383,13 @@ def epoch_seconds(dev, world, rank, epochs=3):
     args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
                            train_scale=False)
     model = Model(args).to(dev)
-    opt = RiemannianSGD(model.parameters(), lr=1e-2 * world)
+    opt = RiemannianSGD(model.parameters(), lr=1e-2 * world, fused=fused)
     idx, gd = idx.to(dev), gd.to(dev)
-    train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=0)
+    train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=0, sync_stats=sync_stats)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for ep in range(1, epochs + 1):
-        loss = train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=ep)
+        loss = train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=ep, sync_stats=sync_stats)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / epochs, loss
 
@@ -402,9 +402,13 @@ def extras(args, world, rank, dev):
         out["upper_n2_riem_pairs_per_s"] = quick_pairs_per_s("upper", 2, "riem", 1 << 22, 1 << 20, dev, world)
         out["spd_n10_pairs_per_s"] = quick_pairs_per_s("spd", 10, "riem", 1 << 18, 1 << 18, dev, world)
         out["bounded_n3_fone_pairs_per_s"] = quick_pairs_per_s("bounded", 3, "fone", 1 << 22, 1 << 20, dev, world)
-        sec, loss = epoch_seconds(dev, world, rank)
+        sec, loss = epoch_seconds(dev, world, rank, fused=True, sync_stats=True)
         out["train_epoch_sec_config1_grid400_upper_riem_n2_b2048"] = sec
         out["train_epoch_final_loss"] = loss
+        sec_h, _ = epoch_seconds(dev, world, rank, fused=False, sync_stats=True)
+        out["train_epoch_sec_config1_host_optimizer"] = sec_h
+        sec_n, _ = epoch_seconds(dev, world, rank, fused=True, sync_stats=False)
+        out["train_epoch_sec_config1_no_per_step_item_sync"] = sec_n
     except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -66,6 +66,18 @@ int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs);
  * the single-kernel path is used. */
 int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
 
+/* Riemannian SGD step on the whole table in one launch: replaces
+ * geoopt.optim.RiemannianSGD.step for the matrix table - egrad2rgrad (sympa/manifolds/upper_half.py:25-40),
+ * retr (siegel_manifold.py:74-87) and projx (upper_half.py:42-66, csym_math.py:252-278) fused per row:
+ *   upper:  X <- X - lr Y GX Y,  Y <- clamp_eig(Y - lr Y GY Y, eps) only when an eigenvalue is <= eps
+ *   spd:    X <- sym(X + U + U X^-1 U / 2),  U = -lr X sym(G) X        (geoopt, parity unpinned)
+ * Rows whose gradient is identically zero are not touched (equivalent to the dense step, which leaves
+ * them bit-identical).  lr_scale: optional device scalar multiplying lr (a clipping coefficient);
+ * projected: optional device counter incremented by the number of rows the projection moved.
+ * kind bounded is not offered here (SYMPA_ERR_UNSUPPORTED): use the host-side implementation. */
+int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
+                    const double* lr_scale, unsigned long long* projected, void* stream);
+
 /* process-wide tuning switches (host side only).  SYMPA_OPT_SPLIT_PATH: 0 (default) = larger matrix
  * sizes run as ONE cooperative kernel; 1 = three kernels through `scratch` (sympa_scratch_bytes then
  * reports a non-zero size).  Results are bit-identical either way. */

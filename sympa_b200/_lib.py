@@ -25,6 +25,7 @@ EXPORTS = (
     "sympa_last_cuda_error",
     "sympa_workspace_bytes",
     "sympa_scratch_bytes",
+    "sympa_rsgd_step",
     "sympa_set_option",
     "sympa_probe_fp64",
     "sympa_dist_forward",
@@ -55,6 +56,8 @@ def load():
     lib.sympa_last_cuda_error.restype = ctypes.c_char_p
     lib.sympa_workspace_bytes.restype = L
     lib.sympa_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_rsgd_step.restype = I
+    lib.sympa_rsgd_step.argtypes = [I, I, L, P, P, D, P, P, P]
     lib.sympa_probe_fp64.restype = L
     lib.sympa_probe_fp64.argtypes = [I, P, P]
     lib.sympa_set_option.restype = I

@@ -41,6 +41,19 @@ struct PairArgs {
 template <int N>
 int launch_pairs(int kind, int mode, const PairArgs& a, cudaStream_t stream);
 
+struct RsgdArgs {
+  int64_t num_rows;
+  double* table;
+  const double* grad;
+  double lr;
+  const double* lr_scale;           // optional device scalar multiplying lr (e.g. a clipping coefficient)
+  unsigned long long* projected;    // optional device counter of rows the projection had to move
+};
+
+// launch the optimizer-row kernel for matrix size N; defined in pair_kernels_n.cu
+template <int N>
+int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t stream);
+
 int check_launch();
 int grid_for(int64_t work_items, int threads, int waves_cap);
 
@@ -281,6 +294,55 @@ static int launch_mode(int mode, const PairArgs& a, cudaStream_t s) {
     case kModeStep: return launch_any<N, KIND, kModeStep>(a, s);
   }
   return 1;
+}
+
+// Riemannian SGD row update (egrad2rgrad + retr + projx fused; upper_half.py:25-66, geoopt RSGD):
+// one thread per table row, rows whose gradient is identically zero are left untouched - which makes
+// the dense launch equivalent to a sparse update of the rows the batch touched.
+template <int N, int KIND>
+__global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
+  constexpr bool REG = N <= SY_REG_MAX_N;
+  constexpr int T = Cfg<N>::kTri;
+  constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;
+  const double lr = a.lr * (a.lr_scale != nullptr ? __ldg(a.lr_scale) : 1.0);
+  unsigned long long moved = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.num_rows; r += stride) {
+    const double* g = a.grad + r * PER;
+    double* p = a.table + r * PER;
+    double gx[T], gy[T];
+    load_packed<N, REG>(g, gx);
+    if (KIND != kSpd) load_packed<N, REG>(g + N * N, gy);
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < T; ++i) any = any || (gx[i] != 0.0) || (KIND != kSpd && gy[i] != 0.0);
+    if (!any) continue;
+    double x[T], y[T];
+    load_packed<N, REG>(p, x);
+    if (KIND == kSpd) {
+      if (REG) reg::spd_rsgd_row<N>(x, gx, lr); else loc::spd_rsgd_row<N>(x, gx, lr);
+      store_full<N, REG>(p, x);
+    } else {
+      load_packed<N, REG>(p + N * N, y);
+      const bool m = REG ? reg::upper_rsgd_row<N>(x, y, gx, gy, lr) : loc::upper_rsgd_row<N>(x, y, gx, gy, lr);
+      moved += m ? 1ull : 0ull;
+      store_full<N, REG>(p, x);
+      store_full<N, REG>(p + N * N, y);
+    }
+  }
+  if (a.projected != nullptr && moved != 0) atomicAdd(a.projected, moved);
+}
+
+template <int N>
+int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t s) {
+  const int grid = grid_for(a.num_rows, kThreads, 16);
+  if (kind == kUpper)
+    rsgd_kernel<N, kUpper><<<grid, kThreads, 0, s>>>(a);
+  else if (kind == kSpd)
+    rsgd_kernel<N, kSpd><<<grid, kThreads, 0, s>>>(a);
+  else
+    return 2;
+  return check_launch();
 }
 
 template <int N>

@@ -137,7 +137,9 @@ int grid_for(int64_t work_items, int threads, int waves_cap) {
   return (int)blocks;
 }
 
-#define SY_DECL(K) extern template int launch_pairs<K>(int, int, const PairArgs&, cudaStream_t);
+#define SY_DECL(K)                                                                  \
+  extern template int launch_pairs<K>(int, int, const PairArgs&, cudaStream_t);     \
+  extern template int launch_rsgd<K>(int, const RsgdArgs&, cudaStream_t);
 SY_DECL(1) SY_DECL(2) SY_DECL(3) SY_DECL(4) SY_DECL(5) SY_DECL(6) SY_DECL(7) SY_DECL(8) SY_DECL(9) SY_DECL(10)
 #undef SY_DECL
 
@@ -146,6 +148,17 @@ static int launch_n(int n, int kind, int mode, const PairArgs& a, cudaStream_t s
 #define SY_CASE(K) \
   case K:          \
     return launch_pairs<K>(kind, mode, a, s);
+    SY_CASE(1) SY_CASE(2) SY_CASE(3) SY_CASE(4) SY_CASE(5) SY_CASE(6) SY_CASE(7) SY_CASE(8) SY_CASE(9) SY_CASE(10)
+#undef SY_CASE
+  }
+  return SYMPA_ERR_UNSUPPORTED;
+}
+
+static int launch_rsgd_n(int n, int kind, const RsgdArgs& a, cudaStream_t s) {
+  switch (n) {
+#define SY_CASE(K) \
+  case K:          \
+    return launch_rsgd<K>(kind, a, s);
     SY_CASE(1) SY_CASE(2) SY_CASE(3) SY_CASE(4) SY_CASE(5) SY_CASE(6) SY_CASE(7) SY_CASE(8) SY_CASE(9) SY_CASE(10)
 #undef SY_CASE
   }
@@ -193,6 +206,22 @@ static int g_split_enabled = 0;
 static bool uses_scratch(int kind, int n) { return g_split_enabled && kind == SYMPA_KIND_UPPER && n > SY_REG_MAX_N; }
 static int64_t scratch_per_pair_bytes(int n) { return (int64_t)(5 * n * n + n) * (int64_t)sizeof(double); }
 static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs * (int64_t)(1 + n) * (int64_t)sizeof(double); }
+
+int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
+                    const double* lr_scale, unsigned long long* projected, void* stream) {
+  if (n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
+  if (kind != SYMPA_KIND_UPPER && kind != SYMPA_KIND_SPD) return SYMPA_ERR_UNSUPPORTED;
+  if (num_rows < 0 || table == nullptr || grad == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (num_rows == 0) return SYMPA_OK;
+  RsgdArgs a = {};
+  a.num_rows = num_rows;
+  a.table = table;
+  a.grad = grad;
+  a.lr = lr;
+  a.lr_scale = lr_scale;
+  a.projected = projected;
+  return launch_rsgd_n(n, kind, a, (cudaStream_t)stream);
+}
 
 int64_t sympa_probe_fp64(int iters, double* out, void* stream) {
   if (iters <= 0 || out == nullptr) return -1;

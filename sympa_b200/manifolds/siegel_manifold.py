@@ -90,6 +90,10 @@ class SiegelManifold(Manifold, ABC):
         if self._projected_dev is not None:
             self._projected += int(self._projected_dev.item())
             self._projected_dev = None
+        counter = getattr(self, "_projected_counter", None)   # rows moved by the fused optimizer kernel
+        if counter is not None:
+            self._projected += int(counter.item())
+            counter.zero_()
         return self._projected
 
     @projected_points.setter

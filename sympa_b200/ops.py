@@ -237,3 +237,17 @@ def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsu
             _ptr(graph_dist), float(scale), _ptr(wsum_w), _ptr(grad_table), _ptr(grad_wsum_w), _ptr(grad_scale),
             _ptr(loss_out), _ptr(dist_out), _ptr(scratch), scratch_bytes, _ptr(status_word(dev)), _stream()))
     return loss_out
+
+
+def rsgd_step(kind, table, grad, lr, lr_scale=None, projected=None):
+    """In-place Riemannian SGD update of a CUDA table (one launch); see sympa_rsgd_step in the header."""
+    lib = _lib.load()
+    if not table.is_cuda or table.dtype != torch.float64 or not table.is_contiguous():
+        raise RuntimeError("sympa_b200: rsgd_step needs a contiguous CUDA float64 table (there is no CPU path)")
+    grad = _require(grad, "grad")
+    n = table.shape[-1]
+    _check_n(n)
+    with torch.cuda.device(table.device):
+        _lib.check(lib.sympa_rsgd_step(_lib.KIND[kind], n, table.shape[0], table.data_ptr(), grad.data_ptr(), float(lr),
+                                       _ptr(lr_scale), _ptr(projected), _stream()))
+    return table

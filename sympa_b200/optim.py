@@ -12,8 +12,11 @@ import torch
 
 
 class RiemannianSGD(torch.optim.Optimizer):
-    def __init__(self, params, lr, weight_decay=0.0, sparse_rows=False):
-        super().__init__(params, dict(lr=lr, weight_decay=weight_decay, sparse_rows=sparse_rows))
+    def __init__(self, params, lr, weight_decay=0.0, sparse_rows=False, fused=False):
+        """fused=True: CUDA tables on the upper / spd manifolds are updated by the one-launch kernel
+        behind sympa_rsgd_step (rows with a zero gradient untouched); everything else takes the torch
+        path below."""
+        super().__init__(params, dict(lr=lr, weight_decay=weight_decay, sparse_rows=sparse_rows, fused=fused))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -32,6 +35,17 @@ class RiemannianSGD(torch.optim.Optimizer):
                     if wd:
                         g = g + wd * p
                     p.add_(g, alpha=-lr)
+                    continue
+                kind = getattr(manifold, "kind", None)
+                if group["fused"] and wd == 0.0 and p.is_cuda and kind in ("upper", "spd") and p.dtype == torch.float64:
+                    from . import ops
+                    counter = None
+                    if kind == "upper":
+                        counter = getattr(manifold, "_projected_counter", None)
+                        if counter is None or counter.device != p.device:
+                            counter = torch.zeros(1, dtype=torch.int64, device=p.device)
+                            manifold._projected_counter = counter
+                    ops.rsgd_step(kind, p.data, g, lr, projected=counter)
                     continue
                 if group["sparse_rows"] and wd == 0.0 and p.dim() >= 3:
                     rows = torch.nonzero(g.reshape(g.shape[0], -1).abs().amax(dim=1) > 0).reshape(-1)

@@ -69,4 +69,14 @@ def hostcheck():
         assert rc == 0
         return dist, vvd, g1, g2, int(st[0])
 
+    def rsgd(variant, kind, n, table, grad, lr):
+        t = np.ascontiguousarray(table, dtype=np.float64).copy()
+        g = np.ascontiguousarray(grad, dtype=np.float64)
+        dll.hostcheck_rsgd.restype = ctypes.c_int64
+        projected = dll.hostcheck_rsgd(variant, {"upper": 0, "bounded": 1, "spd": 2}[kind], n, ctypes.c_int64(t.shape[0]),
+                                       P(t.ctypes.data), P(g.ctypes.data), ctypes.c_double(lr))
+        assert projected >= 0
+        return t, int(projected)
+
+    run.rsgd = rsgd
     return run

@@ -169,3 +169,58 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
   }
   return 1;
 }
+
+// ---- optimizer rows -------------------------------------------------------------------------
+#define HC_RSGD(NS)                                                                                          \
+  template <int N>                                                                                           \
+  static int64_t rsgd_##NS(int kind, int64_t rows, double* table, const double* grad, double lr) {           \
+    constexpr int T = Cfg<N>::kTri;                                                                          \
+    int64_t projected = 0;                                                                                   \
+    const int per = (kind == kSpd ? 1 : 2) * N * N;                                                          \
+    for (int64_t r = 0; r < rows; ++r) {                                                                     \
+      double* p = table + r * per;                                                                           \
+      const double* g = grad + r * per;                                                                      \
+      if (kind == kSpd) {                                                                                    \
+        double x[T], gx[T];                                                                                  \
+        NS::pack_sym<N>(p, x);                                                                               \
+        NS::pack_sym<N>(g, gx);                                                                              \
+        NS::spd_rsgd_row<N>(x, gx, lr);                                                                      \
+        for (int i = 0; i < N; ++i)                                                                          \
+          for (int j = 0; j < N; ++j) p[i * N + j] = x[tri(i, j)];                                           \
+      } else {                                                                                               \
+        double x[T], y[T], gx[T], gy[T];                                                                     \
+        NS::pack_sym<N>(p, x);                                                                               \
+        NS::pack_sym<N>(p + N * N, y);                                                                       \
+        NS::pack_sym<N>(g, gx);                                                                              \
+        NS::pack_sym<N>(g + N * N, gy);                                                                      \
+        projected += NS::upper_rsgd_row<N>(x, y, gx, gy, lr) ? 1 : 0;                                        \
+        for (int i = 0; i < N; ++i)                                                                          \
+          for (int j = 0; j < N; ++j) {                                                                      \
+            p[i * N + j] = x[tri(i, j)];                                                                     \
+            p[N * N + i * N + j] = y[tri(i, j)];                                                             \
+          }                                                                                                  \
+      }                                                                                                      \
+    }                                                                                                        \
+    return projected;                                                                                        \
+  }
+HC_RSGD(reg)
+HC_RSGD(loc)
+
+extern "C" int64_t hostcheck_rsgd(int variant, int kind, int n, int64_t rows, double* table, const double* grad,
+                                  double lr) {
+  if (kind == kBounded) return -1;
+  if (variant == 0) {
+    switch (n) {
+#define CASE(K) case K: return rsgd_reg<K>(kind, rows, table, grad, lr);
+      CASE(1) CASE(2) CASE(3) CASE(4)
+#undef CASE
+    }
+    return -1;
+  }
+  switch (n) {
+#define CASE(K) case K: return rsgd_loc<K>(kind, rows, table, grad, lr);
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+  }
+  return -1;
+}

@@ -62,3 +62,33 @@ def test_graph_triplets_match_known_sizes():
     # siblings 1 and 2 are at distance 2, root to a leaf at distance 5
     lookup = {(int(a), int(b)): float(x) for (a, b), x in zip(idx.tolist(), d.tolist())}
     assert lookup[(1, 2)] == 2.0 and lookup[(0, 363)] == 5.0 and lookup[(1, 4)] == 1.0
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 10])
+@pytest.mark.parametrize("lr", [1e-2, 5.0])
+def test_row_update_templates_match_oracle_upper(hostcheck, n, lr):
+    """the per-row C++ templates behind sympa_rsgd_step (egrad2rgrad + retr + projx fused) against the
+    oracle's restatement of upper_half.py:25-66"""
+    table, grad, touched = make("upper", 40, n, 11 + n)
+    ref = so.rsgd_step("upper", table, grad, lr)
+    moved_ref = int((~torch.all(torch.linalg.eigvalsh((table - lr * so.upper_egrad2rgrad(table, grad))[:, 1]) > 1e-5, dim=-1)).sum())
+    for variant in ((0, 1) if n <= 4 else (1,)):
+        out, projected = hostcheck.rsgd(variant, "upper", n, table.numpy(), grad.numpy(), lr)
+        torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-9, atol=1e-11)
+        assert projected == moved_ref
+        if lr > 1:
+            assert projected > 0
+
+
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_row_update_templates_match_oracle_spd(hostcheck, n):
+    g = torch.Generator().manual_seed(3)
+    x = so.spd_spread(25, n, generator=g)
+    gr = torch.randn(25, n, n, dtype=torch.float64, generator=g)
+    gr = 0.5 * (gr + gr.transpose(-1, -2))
+    lr = 0.05
+    u = -lr * (x @ gr @ x)
+    ref = so.sym(x + u + 0.5 * u @ torch.linalg.solve(x, u))
+    for variant in ((0, 1) if n <= 4 else (1,)):
+        out, _ = hostcheck.rsgd(variant, "spd", n, x.numpy(), gr.numpy(), lr)
+        torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-11, atol=1e-13)

@@ -318,3 +318,60 @@ def test_train_epoch_matches_oracle_loop(sb, kind, metric, n):
         steps += 1
     np.testing.assert_allclose(mean_loss, total / steps, rtol=1e-7)
     torch.testing.assert_close(model.embeddings.embeds.detach().cpu(), table, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 2), ("upper", 3), ("upper", 4), ("upper", 6), ("upper", 10), ("spd", 3), ("spd", 6)])
+@pytest.mark.parametrize("lr", [1e-2, 5.0])
+def test_fused_rsgd_step_matches_host_optimizer(sb, kind, n, lr):
+    """sympa_rsgd_step (one launch: egrad2rgrad + retr + projx per row) against the torch implementation
+    of the same update and against the oracle's restatement of the reference (upper_half.py:25-66)."""
+    from sympa_b200.embeddings import ManifoldParameter
+    from sympa_b200.optim import RiemannianSGD
+    g = torch.Generator().manual_seed(5 + n)
+    rows = 300
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g)
+        man = sb.SymmetricPositiveDefinite()
+        lr = min(lr, 0.05)
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        man = sb.UpperHalfManifold(dims=n)
+    grad = torch.zeros_like(table)
+    touched = torch.randperm(rows, generator=g)[: rows // 3]
+    gr = torch.randn((len(touched),) + tuple(table.shape[1:]), dtype=torch.float64, generator=g)
+    grad[touched] = 0.5 * (gr + gr.transpose(-1, -2))
+    out = {}
+    for fused in (False, True):
+        p = ManifoldParameter(table.clone().cuda(), manifold=man)
+        p.grad = grad.clone().cuda()
+        RiemannianSGD([p], lr=lr, fused=fused).step()
+        out[fused] = p.detach().cpu()
+    torch.testing.assert_close(out[True], out[False], rtol=1e-9, atol=1e-11)
+    untouched = torch.ones(rows, dtype=torch.bool)
+    untouched[touched] = False
+    assert torch.equal(out[True][untouched], table[untouched])
+    if kind == "upper":
+        torch.testing.assert_close(out[True], so.rsgd_step("upper", table, grad, lr), rtol=1e-9, atol=1e-11)
+        if lr > 1:
+            assert man.projected_points > 0
+
+
+def test_training_with_fused_optimizer_equals_host_optimizer(sb):
+    from types import SimpleNamespace
+    from sympa_b200.graphs import balanced_tree_triplets
+    from sympa_b200.model import Model
+    from sympa_b200.optim import RiemannianSGD
+    from sympa_b200.runner import train_epoch
+    idx, gd, nodes = balanced_tree_triplets(3, 3)
+    args = SimpleNamespace(manifold="upper", metric="fone", dims=3, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                           train_scale=False)
+    res = {}
+    for fused in (False, True):
+        torch.manual_seed(1)
+        model = Model(args).cuda()
+        opt = RiemannianSGD(model.parameters(), lr=5e-2, fused=fused)
+        losses = [train_epoch(model, opt, idx.cuda(), gd.cuda(), 128, epoch=e, sync_stats=not fused) for e in range(3)]
+        res[fused] = (losses, model.embeddings.embeds.detach().cpu())
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=1e-8)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-7, atol=1e-10)
+    assert res[True][0][-1] < res[True][0][0]      # it trains
