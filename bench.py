@@ -293,12 +293,19 @@ def run_ours(args):
 
     peaks, peak_kind = load_peaks()
     fp64_peak = measure_fp64_peak(dev)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(f"{kind}_n{n}_fwdsave")
+        if rec:
+            traffic = rec["bytes_per_pair"] * b     # ncu dram bytes per pair x pairs of one launch
     abytes = algorithmic_bytes_per_pair(kind, n) * b
     achieved = abytes / (fwd * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": f"pair_kernel<{n},{kind},fwd+unit-grad>", "achieved": round(achieved, 2),
         "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-        "traffic": None, "kernel_ms": round(fwd, 4), "scatter_kernel_ms": round(bwd, 4),
+        "traffic": traffic, "traffic_source": "ncu --set full capture, see profiles/r01_traffic.json",
+        "algorithmic_bytes": abytes, "kernel_ms": round(fwd, 4), "scatter_kernel_ms": round(bwd, 4),
         "fp64": {"achieved_lean_tflops": round(lean_flops_per_pair(n) * b / (fwd * 1e-3) / 1e12, 3),
                  "peak_measured_tflops": round(fp64_peak, 2), "peak_nominal_tflops": 37.2,
                  "frac_of_measured": round(lean_flops_per_pair(n) * b / (fwd * 1e-3) / 1e12 / max(fp64_peak, 1e-9), 4),
