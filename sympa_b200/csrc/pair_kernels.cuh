@@ -59,7 +59,16 @@ int grid_for(int64_t work_items, int threads, int waves_cap);
 
 #ifdef SYMPA_PAIR_KERNELS_IMPL
 
-constexpr int kThreads = 128;
+#ifndef SY_PAIR_THREADS
+#define SY_PAIR_THREADS 128
+#endif
+constexpr int kThreads = SY_PAIR_THREADS;
+// Re-align the warps of a CTA once per pair (one __syncthreads per ~10k instructions): the fully
+// unrolled body is several times larger than the instruction cache, and warps that walk through it
+// together share their instruction fetches.
+#ifndef SY_BLOCK_SYNC
+#define SY_BLOCK_SYNC 1
+#endif
 // minimum resident CTAs per SM asked of ptxas for the register-resident sizes n = 3, 4 (caps the
 // registers per thread: 2 -> 255, 3 -> 168, 4 -> 128); tuned on the B200, see DESIGN.md
 #ifndef SY_REG_MIN_BLOCKS
@@ -164,7 +173,10 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
     for (int k = 0; k < N; ++k) gw_acc[k] = 0.0;
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.num_pairs; p += stride) {
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.num_pairs; base += stride) {
+    if (SY_BLOCK_SYNC && REG) __syncthreads();
+    const int64_t p = base + threadIdx.x;
+    if (p >= a.num_pairs) continue;   // (the barrier above is reached by every thread of the CTA each iteration)
     const double* p1;
     const double* p2;
     int64_t i1 = 0, i2 = 0;
