@@ -5,6 +5,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// CTA-wide re-alignment of the warps between the phases of a pair, for the sizes whose fully unrolled
+// body is much larger than the instruction cache (n >= 4): see pair_kernel.
+#ifndef SY_BLOCK_SYNC
+#define SY_BLOCK_SYNC 1
+#endif
+#if defined(SYMPA_PAIR_KERNELS_IMPL) && SY_BLOCK_SYNC
+#define SY_PHASE_SYNC_REG(N) \
+  if ((N) >= 4) __syncthreads();
+#endif
 #include "pair_math.cuh"
 
 namespace sympa {
@@ -63,12 +72,12 @@ int grid_for(int64_t work_items, int threads, int waves_cap);
 #define SY_PAIR_THREADS 128
 #endif
 constexpr int kThreads = SY_PAIR_THREADS;
-// Re-align the warps of a CTA once per pair (one __syncthreads per ~10k instructions): the fully
-// unrolled body is several times larger than the instruction cache, and warps that walk through it
-// together share their instruction fetches.
-#ifndef SY_BLOCK_SYNC
-#define SY_BLOCK_SYNC 1
-#endif
+// Re-align the warps of a CTA at the start of every pair and after its Jacobi sweeps (two
+// __syncthreads per ~10k instructions): the fully unrolled body is several times larger than the
+// instruction cache, and warps that walk through it together share their instruction fetches
+// (measured on the B200: n = 4 forward+gradient kernel 4.06 -> 2.9 ms per 4M pairs; n = 3 fits and
+// does not profit).  Every thread of the CTA therefore runs every iteration: threads without a pair
+// (tail, bad index) recompute a valid one and skip the writes.
 // minimum resident CTAs per SM asked of ptxas for the register-resident sizes n = 3, 4 (caps the
 // registers per thread: 2 -> 255, 3 -> 168, 4 -> 128); tuned on the B200, see DESIGN.md
 #ifndef SY_REG_MIN_BLOCKS
@@ -174,9 +183,10 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.num_pairs; base += stride) {
-    if (SY_BLOCK_SYNC && REG) __syncthreads();
-    const int64_t p = base + threadIdx.x;
-    if (p >= a.num_pairs) continue;   // (the barrier above is reached by every thread of the CTA each iteration)
+    if (SY_BLOCK_SYNC && REG && N >= 4) __syncthreads();
+    int64_t p = base + threadIdx.x;
+    bool active = p < a.num_pairs;
+    if (!active) p = a.num_pairs - 1;
     const double* p1;
     const double* p2;
     int64_t i1 = 0, i2 = 0;
@@ -185,9 +195,13 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
       i1 = ij.x;
       i2 = ij.y;
       if (i1 < 0 || i1 >= a.num_rows || i2 < 0 || i2 >= a.num_rows) {
-        st |= kStatusBadIndex;
-        if (a.dist_out) a.dist_out[p] = 0.0;
-        continue;
+        if (active) {
+          st |= kStatusBadIndex;
+          if (a.dist_out) a.dist_out[p] = 0.0;
+        }
+        active = false;
+        i1 = 0;
+        i2 = 0;
       }
       p1 = a.table + i1 * PER;
       p2 = a.table + i2 * PER;
@@ -197,12 +211,13 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
     }
     double vs[N];
     double dist;
+    unsigned stp = 0;  // status of this pair; dropped when the thread only recomputes a stand-in pair
     double g1r[GRAD ? T : 1], g1i[GRAD ? T : 1], g2r[GRAD ? T : 1], g2i[GRAD ? T : 1];
     if (KIND == kSpd) {
       double x[T], y[T];
       load_packed<N, REG>(p1, x);
       load_packed<N, REG>(p2, y);
-      dist = M::template spd<N, GRAD>(x, y, vs, g1r, g2r, &st);
+      dist = M::template spd<N, GRAD>(x, y, vs, g1r, g2r, &stp);
     } else {
       double x1[T], y1[T], x2[T], y2[T];
       load_packed<N, REG>(p1, x1);
@@ -210,16 +225,17 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
       load_packed<N, REG>(p2, x2);
       load_packed<N, REG>(p2 + N * N, y2);
       if (KIND == kUpper)
-        dist = M::template upper<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &st);
+        dist = M::template upper<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &stp);
       else
-        dist = M::template bounded<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &st);
+        dist = M::template bounded<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &stp);
     }
-    if (a.dist_out) a.dist_out[p] = dist;
-    if (a.vvd_out) {
+    if (active) st |= stp;
+    if (active && a.dist_out) a.dist_out[p] = dist;
+    if (active && a.vvd_out) {
 #pragma unroll
       for (int k = 0; k < N; ++k) a.vvd_out[p * N + k] = vs[k];
     }
-    if (MODE == kModeFwdSave) {
+    if (active && MODE == kModeFwdSave) {
       double* o1 = a.gz1 + p * PER;
       double* o2 = a.gz2 + p * PER;
       store_full<N, REG>(o1, g1r);
@@ -229,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
         store_full<N, REG>(o2 + N * N, g2i);
       }
     }
-    if (MODE == kModeStep) {
+    if (active && MODE == kModeStep) {
       // L_p = |(s d / g)^2 - 1|   (sympa/losses.py:16-19 with the scale of sympa/model.py:30)
       const double gd = __ldg(a.graph_dist + p);
       const double r = a.scale * dist / gd;
