@@ -26,23 +26,48 @@ struct CoopCfg {
   static constexpr int kSmemBytes = PW * L::kDoubles * (int)sizeof(double);
 };
 
+// per-kind view of a pair's shared-memory region: size, where the scalars are, where the four
+// gradient blocks (re/im of operand 1 and 2) are and with which sign
+template <int N, int KIND>
+struct CoopTraits;
+template <int N>
+struct CoopTraits<N, kUpper> {
+  typedef coop::Layout<N> L;
+  static constexpr int kDoubles = L::kDoubles, DIST = L::DIST, VS = L::VS, FLAG = L::FLAG;
+  static constexpr int R1 = L::GX2, I1 = L::GY1, R2 = L::GX2, I2 = L::GY2;
+  static constexpr double kSignR1 = -1.0;  // d/dX1 = -d/dX2
+};
+template <int N>
+struct CoopTraits<N, kSpd> {
+  typedef coop::SpdLayout<N> L;
+  static constexpr int kDoubles = L::kDoubles, DIST = L::DIST, VS = L::VS, FLAG = L::FLAG;
+  static constexpr int R1 = L::SPD_GX, I1 = L::SPD_GX, R2 = L::SPD_GY, I2 = L::SPD_GY;
+  static constexpr double kSignR1 = 1.0;
+};
+template <int N>
+struct CoopTraits<N, kBounded> {
+  typedef coop::BoundedLayout<N> L;
+  static constexpr int kDoubles = L::kDoubles, DIST = L::DIST, VS = L::VS, FLAG = L::FLAG;
+  static constexpr int R1 = L::G1R, I1 = L::G1I, R2 = L::G2R, I2 = L::G2I;
+  static constexpr double kSignR1 = 1.0;
+};
+
 // writes the unit gradients (MODE fwd+save) or the scaled scatter-add (MODE step) from the results the
 // pair mathematics left in shared memory (symmetrised here)
 template <int N, int KIND, int MODE>
 __device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* sm, int g, int64_t p, int64_t i1,
                                                int64_t i2, double dist, double* loss_acc, double* gscale_acc) {
+  typedef CoopTraits<N, KIND> TR;
   typedef coop::Layout<N> L;
-  typedef coop::SpdLayout<N> S;
   constexpr int G = L::G;
   constexpr int NN = N * N;
   constexpr int PER = (KIND == kSpd ? 1 : 2) * NN;
   constexpr int LD = L::LD;
-  // upper: (re1, im1, re2, im2) = (-GX2, GY1, GX2, GY2);  spd: (re1, re2) = (GX, GY)
-  const double* r1 = sm + (KIND == kSpd ? S::SPD_GX : L::GX2);
-  const double* r2 = sm + (KIND == kSpd ? S::SPD_GY : L::GX2);
-  const double s1 = (KIND == kSpd) ? 1.0 : -1.0;
-  const double* m1 = sm + L::GY1;
-  const double* m2 = sm + L::GY2;
+  const double* r1 = sm + TR::R1;
+  const double* r2 = sm + TR::R2;
+  const double s1 = TR::kSignR1;
+  const double* m1 = sm + TR::I1;
+  const double* m2 = sm + TR::I2;
   double scale = 1.0;
   double* o1;
   double* o2;
@@ -90,8 +115,7 @@ __device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* 
 
 template <int N, int KIND, int MODE>
 __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
-  static_assert(KIND == kUpper || KIND == kSpd, "cooperative kernel: upper half space and spd");
-  typedef coop::Layout<N> L;
+  typedef CoopTraits<N, KIND> L;
   constexpr int G = CoopCfg<N>::G;
   constexpr int PW = CoopCfg<N>::PW;
   constexpr int NN = N * N;
@@ -131,6 +155,8 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
     WarpExec ex{g, active};
     if (KIND == kSpd)
       coop::spd_pair<N, GRAD>(ex, sm, p1, p2);
+    else if (KIND == kBounded)
+      coop::bounded_pair<N, GRAD>(ex, sm, p1, p2, a.metric, a.wsum_w);
     else
       coop::upper_pair<N, GRAD>(ex, sm, p1, p2, a.metric, a.wsum_w);
     if (active) {
@@ -354,7 +380,7 @@ static int launch_split(const PairArgs& a, double* scratch, int64_t cap, cudaStr
 template <int N, int KIND, int MODE>
 static int launch_coop(const PairArgs& a, cudaStream_t s) {
   constexpr int PW = CoopCfg<N>::PW;
-  constexpr int smem = CoopCfg<N>::kSmemBytes;
+  constexpr int smem = PW * CoopTraits<N, KIND>::kDoubles * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(coop_kernel<N, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

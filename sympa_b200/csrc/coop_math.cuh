@@ -407,8 +407,35 @@ SY_HD void metric_tail(Ex& ex, double* sm, int metric, const double* wsum_w, int
 //   w_from_pq + jacobi + sigma + metric_tail : W -> Takagi values -> vvd, dist, backward coefficients
 //   upper_backward : unit gradients                                          (sm[GX2], sm[GY2], sm[GY1])
 // p1 / p2 point at the (2, n, n) rows in global memory.
-template <int N, class Ex>
-SY_HD void upper_prologue(Ex& ex, double* sm, const double* p1, const double* p2) {
+// Where the upper-half operands D = X2 - X1, Y1, Y2 come from: straight from the two (2, n, n) rows
+// in global memory (symmetrised on the fly) ...
+template <int N>
+struct GlobalIn {
+  static constexpr bool kResetFlag = true;
+  const double* p1;
+  const double* p2;
+  SY_HD double d(int e, int et, int) const {
+    return 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
+  }
+  SY_HD double y1(int e, int et, int, bool) const { return 0.5 * (SY_LDG(p1 + N * N + e) + SY_LDG(p1 + N * N + et)); }
+  SY_HD double y2(int e, int et, int, bool) const { return 0.5 * (SY_LDG(p2 + N * N + e) + SY_LDG(p2 + N * N + et)); }
+};
+// ... or, for the bounded domain, from the inverse Cayley transforms kept in shared memory:
+//   Z_k = i (2 N_k - I),  N_k = (I - z_k)^-1 = U_k + i V_k   ->   X_k = -2 V_k,  Y_k = 2 U_k - I
+template <int N>
+struct CayleyIn {
+  static constexpr bool kResetFlag = false;  // the flag already carries the status of the Cayley inverses
+  const double* u1;
+  const double* v1;
+  const double* u2;
+  const double* v2;
+  SY_HD double d(int, int, int s) const { return -2.0 * (v2[s] - v1[s]); }
+  SY_HD double y1(int, int, int s, bool diag) const { return 2.0 * u1[s] - (diag ? 1.0 : 0.0); }
+  SY_HD double y2(int, int, int s, bool diag) const { return 2.0 * u2[s] - (diag ? 1.0 : 0.0); }
+};
+
+template <int N, class In, class Ex>
+SY_HD void upper_prologue(Ex& ex, double* sm, const In& in) {
   typedef Layout<N> L;
   constexpr int G = L::G;
   constexpr int NN = L::NN;
@@ -425,12 +452,12 @@ SY_HD void upper_prologue(Ex& ex, double* sm, const double* p1, const double* p2
   (void)G; (void)NN; (void)LD; (void)li; (void)a0; (void)a1; (void)a2; (void)a3; (void)a4; (void)a5; (void)rd; (void)flag;
   // ---- load: a0 = D = X2 - X1, a1 = Y1, a2 = Y2 (symmetrised)
   SY_STAGE_BEGIN(ex)
-  if (g == 0) *flag = 0.0;
+  if (g == 0 && In::kResetFlag) *flag = 0.0;
   for (int e = g; e < NN; e += G) {
     const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
-    a0[s] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
-    a1[s] = 0.5 * (SY_LDG(p1 + NN + e) + SY_LDG(p1 + NN + et));
-    a2[s] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
+    a0[s] = in.d(e, et, s);
+    a1[s] = in.y1(e, et, s, i == j);
+    a2[s] = in.y2(e, et, s, i == j);
   }
   SY_STAGE_END(ex)
 
@@ -487,8 +514,8 @@ SY_HD void spectrum(Ex& ex, double* sm, int metric, const double* wsum_w) {
 }
 
 // backward: needs sm[LI], P = sm[PBUF], Q = sm[QBUF], G = (sm[GR], sm[GI]) column-major, sm[COEF]
-template <int N, class Ex>
-SY_HD void upper_backward(Ex& ex, double* sm, const double* p1, const double* p2) {
+template <int N, class In, class Ex>
+SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   typedef Layout<N> L;
   constexpr int G = L::G;
   constexpr int NN = L::NN;
@@ -614,8 +641,8 @@ SY_HD void upper_backward(Ex& ex, double* sm, const double* p1, const double* p2
   SY_STAGE_BEGIN(ex)
   for (int e = g; e < NN; e += G) {
     const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
-    a0[s] = 0.5 * ((SY_LDG(p2 + e) + SY_LDG(p2 + et)) - (SY_LDG(p1 + e) + SY_LDG(p1 + et)));
-    a4[s] = 0.5 * (SY_LDG(p2 + NN + e) + SY_LDG(p2 + NN + et));
+    a0[s] = in.d(e, et, s);
+    a4[s] = in.y2(e, et, s, i == j);
   }
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
@@ -701,7 +728,8 @@ template <int N, class Ex>
 SY_HD void split_prologue(Ex& ex, double* sm, const double* p1, const double* p2, double* scratch, int64_t cap,
                           int64_t slot) {
   typedef Layout<N> L;
-  upper_prologue<N>(ex, sm, p1, p2);
+  const GlobalIn<N> in{p1, p2};
+  upper_prologue<N>(ex, sm, in);
   park<N>(ex, sm + L::LI, Scratch<N>::li(scratch, cap, slot));
   park<N>(ex, sm + L::PBUF, Scratch<N>::pb(scratch, cap, slot));
   park<N>(ex, sm + L::QBUF, Scratch<N>::qb(scratch, cap, slot));
@@ -737,17 +765,161 @@ SY_HD void split_backward(Ex& ex, double* sm, const double* p1, const double* p2
   SY_STAGE_BEGIN(ex)
   for (int k = g; k < N; k += L::G) sm[L::COEF + k] = Scratch<N>::coef(scratch, cap, slot)[k];
   SY_STAGE_END(ex)
-  upper_backward<N>(ex, sm, p1, p2);
+  const GlobalIn<N> in{p1, p2};
+  upper_backward<N>(ex, sm, in);
 }
 
 // fused: everything in one go (what the single-kernel path and the forward-only path use)
 template <int N, bool GRAD, class Ex>
 SY_HD void upper_pair(Ex& ex, double* sm, const double* p1, const double* p2, int metric, const double* wsum_w) {
   typedef Layout<N> L;
-  upper_prologue<N>(ex, sm, p1, p2);
+  const GlobalIn<N> in{p1, p2};
+  upper_prologue<N>(ex, sm, in);
   w_from_pq<N>(ex, sm + L::PBUF, sm + L::QBUF, L::LD, sm + L::GR, sm + L::GI);
   spectrum<N, L>(ex, sm, metric, wsum_w);
-  if (GRAD) upper_backward<N>(ex, sm, p1, p2);
+  if (GRAD) upper_backward<N>(ex, sm, in);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bounded domain, one pair, cooperative (bounded_domain.py:27-39): inverse Cayley transform of both
+// operands by the same two-real-solves inverse, the upper half space pipeline on operands that live
+// in shared memory, and the chain rule back through N_k = (I - z_k)^-1:
+//   G_zk = conj(N_k) (2 G_Yk - 2i G_Xk) conj(N_k),  conj(N_k) = U_k - i V_k.
+// Five buffers more than the upper half space layout (U1, V1, U2, V2 and a spare).
+// Results: sm[DIST], sm[VS..], sm[FLAG]; GRAD: d dist / d z1 = (sm[G1R], sm[G1I]), d/dz2 = (sm[G2R], sm[G2I]).
+template <int N>
+struct BoundedLayout {
+  typedef Layout<N> L;
+  static constexpr int NN = L::NN, LD = L::LD, BUF = L::BUF, G = L::G;
+  // memory: [U1 | V1 | U2 | V2 | SP] followed by a complete Layout<N> window (7 buffers + small state),
+  // on which the shared upper-half pipeline runs unchanged
+  static constexpr int U1 = 0, V1 = BUF, U2 = 2 * BUF, V2 = 3 * BUF, SP = 4 * BUF, UP = 5 * BUF;
+  static constexpr int DIST = UP + L::DIST, VS = UP + L::VS, FLAG = UP + L::FLAG;
+  static constexpr int G1R = UP + L::A3, G1I = SP, G2R = UP + L::A5, G2I = UP + L::LI;
+  static constexpr int kRaw = UP + L::kRaw;
+  static constexpr int kDoubles = (kRaw % 2 == 0) ? kRaw + 1 : kRaw;
+};
+
+template <int N, bool GRAD, class Ex>
+SY_HD void bounded_pair(Ex& ex, double* sm, const double* p1, const double* p2, int metric, const double* wsum_w) {
+  typedef BoundedLayout<N> BL;
+  typedef Layout<N> L;
+  constexpr int G = BL::G;
+  constexpr int NN = BL::NN;
+  constexpr int LD = BL::LD;
+  double* up = sm + BL::UP;  // Layout<N> window: 7 buffers + small state
+  double* u1 = sm + BL::U1, *v1 = sm + BL::V1, *u2 = sm + BL::U2, *v2 = sm + BL::V2, *sp = sm + BL::SP;
+  double* a0 = up + L::A0, *a1 = up + L::A1, *a2 = up + L::A2, *a3 = up + L::A3, *a4 = up + L::A4, *a5 = up + L::A5;
+  double* li = up + L::LI;
+  double* rd = up + L::RD;
+  double* flag = up + L::FLAG;
+
+  SY_STAGE_BEGIN(ex)
+  if (g == 0) *flag = 0.0;
+  SY_STAGE_END(ex)
+  for (int k = 0; k < 2; ++k) {
+    const double* z = k == 0 ? p1 : p2;
+    double* u = k == 0 ? u1 : u2;
+    double* v = k == 0 ? v1 : v2;
+    SY_STAGE_BEGIN(ex)
+    for (int e = g; e < NN; e += G) {
+      const int i = e / N, j = e - i * N, et = j * N + i, s = i * LD + j;
+      a0[s] = ((i == j) ? 1.0 : 0.0) - 0.5 * (SY_LDG(z + e) + SY_LDG(z + et));  // E = I - Re z
+      a1[s] = -0.5 * (SY_LDG(z + NN + e) + SY_LDG(z + NN + et));                  // F = -Im z
+    }
+    SY_STAGE_END(ex)
+    inv_spd_real<N>(ex, a0, a1, u, v, a2, a3, a4, rd, flag);
+  }
+  const CayleyIn<N> in{u1, v1, u2, v2};
+  upper_prologue<N>(ex, up, in);
+  w_from_pq<N>(ex, up + L::PBUF, up + L::QBUF, L::LD, up + L::GR, up + L::GI);
+  spectrum<N, L>(ex, up, metric, wsum_w);
+  if (!GRAD) return;
+  upper_backward<N>(ex, up, in);
+  // upper results: G_X2 = a4, G_Y2 = a3, G_Y1 = a0, G_X1 = -a4.   Free: a1, a2, a5, li.
+  // operand 2:  Gamma = 2 G_Y2 - 2i G_X2;  T = conj(N2) Gamma -> (a1, a2)
+  SY_STAGE_BEGIN(ex)
+  const int j0 = g, j1 = g + G;
+  double x0[N], x1[N], y0[N], y1[N], z0[N], z1[N], w0[N], w1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  zero2<N>(z0, z1);
+  zero2<N>(w0, w1);
+  mm_cols<N, false, false>(u2, a3, j0, j1, x0, x1);  // U Gy
+  mm_cols<N, false, false>(v2, a4, j0, j1, y0, y1);  // V Gx
+  mm_cols<N, false, false>(u2, a4, j0, j1, z0, z1);  // U Gx
+  mm_cols<N, false, false>(v2, a3, j0, j1, w0, w1);  // V Gy
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    // (U - iV)(2Gy - 2iGx) = 2(U Gy - V Gx) - 2i(U Gx + V Gy)
+    a1[i * LD + j0] = 2.0 * (x0[i] - y0[i]);
+    a2[i * LD + j0] = -2.0 * (z0[i] + w0[i]);
+    if (j1 < N) {
+      a1[i * LD + j1] = 2.0 * (x1[i] - y1[i]);
+      a2[i * LD + j1] = -2.0 * (z1[i] + w1[i]);
+    }
+  }
+  SY_STAGE_END(ex)
+  // G_z2 = T conj(N2) = (Tr + iTi)(U - iV) = (Tr U + Ti V) + i(Ti U - Tr V) -> (a5, li)
+  SY_STAGE_BEGIN(ex)
+  const int j0 = g, j1 = g + G;
+  double x0[N], x1[N], y0[N], y1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  mm_cols<N, false, false>(a1, u2, j0, j1, x0, x1);
+  mm_cols<N, false, false>(a2, v2, j0, j1, x0, x1);
+  mm_cols<N, false, false>(a2, u2, j0, j1, y0, y1);
+  put_cols<N>(a5, j0, j1, x0, x1, 1.0, 0.0);
+  double z0[N], z1[N];
+  zero2<N>(z0, z1);
+  mm_cols<N, false, false>(a1, v2, j0, j1, z0, z1);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    li[i * LD + j0] = y0[i] - z0[i];
+    if (j1 < N) li[i * LD + j1] = y1[i] - z1[i];
+  }
+  SY_STAGE_END(ex)
+  // operand 1:  Gamma = 2 G_Y1 - 2i G_X1 = 2 a0 + 2i a4;  T = conj(N1) Gamma -> (a1, a2)
+  SY_STAGE_BEGIN(ex)
+  const int j0 = g, j1 = g + G;
+  double x0[N], x1[N], y0[N], y1[N], z0[N], z1[N], w0[N], w1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  zero2<N>(z0, z1);
+  zero2<N>(w0, w1);
+  mm_cols<N, false, false>(u1, a0, j0, j1, x0, x1);  // U Gy
+  mm_cols<N, false, false>(v1, a4, j0, j1, y0, y1);  // V Gx2
+  mm_cols<N, false, false>(u1, a4, j0, j1, z0, z1);  // U Gx2
+  mm_cols<N, false, false>(v1, a0, j0, j1, w0, w1);  // V Gy
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    // (U - iV)(2Gy + 2iGx2) = 2(U Gy + V Gx2) + 2i(U Gx2 - V Gy)
+    a1[i * LD + j0] = 2.0 * (x0[i] + y0[i]);
+    a2[i * LD + j0] = 2.0 * (z0[i] - w0[i]);
+    if (j1 < N) {
+      a1[i * LD + j1] = 2.0 * (x1[i] + y1[i]);
+      a2[i * LD + j1] = 2.0 * (z1[i] - w1[i]);
+    }
+  }
+  SY_STAGE_END(ex)
+  // G_z1 = T conj(N1) -> (a3, sp)
+  SY_STAGE_BEGIN(ex)
+  const int j0 = g, j1 = g + G;
+  double x0[N], x1[N], y0[N], y1[N], z0[N], z1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  zero2<N>(z0, z1);
+  mm_cols<N, false, false>(a1, u1, j0, j1, x0, x1);
+  mm_cols<N, false, false>(a2, v1, j0, j1, x0, x1);
+  mm_cols<N, false, false>(a2, u1, j0, j1, y0, y1);
+  mm_cols<N, false, false>(a1, v1, j0, j1, z0, z1);
+  put_cols<N>(a3, j0, j1, x0, x1, 1.0, 0.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    sp[i * LD + j0] = y0[i] - z0[i];
+    if (j1 < N) sp[i * LD + j1] = y1[i] - z1[i];
+  }
+  SY_STAGE_END(ex)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,8 +11,13 @@
 #define SY_BLOCK_SYNC 1
 #endif
 #if defined(SYMPA_PAIR_KERNELS_IMPL) && SY_BLOCK_SYNC
-#define SY_PHASE_SYNC_REG(N) \
-  if ((N) >= 4) __syncthreads();
+template <int N>
+__host__ __device__ __forceinline__ void sy_phase_sync() {
+#if defined(__CUDA_ARCH__)
+  if (N >= 4) __syncthreads();
+#endif
+}
+#define SY_PHASE_SYNC_REG(N) sy_phase_sync<N>();
 #endif
 #include "pair_math.cuh"
 
@@ -307,7 +312,7 @@ static int launch_any(const PairArgs& a, cudaStream_t s) {
   if constexpr (KIND == kUpper && (N > SY_REG_MAX_N)) {
     if (a.scratch != nullptr && a.scratch_pairs > 0) return launch_split<N, MODE>(a, a.scratch, a.scratch_pairs, s);
     return launch_coop<N, KIND, MODE>(a, s);
-  } else if constexpr (KIND == kSpd && (N > SY_REG_MAX_N)) {
+  } else if constexpr (N > SY_REG_MAX_N) {   // spd, bounded
     return launch_coop<N, KIND, MODE>(a, s);
   } else {
     return launch_one<N, KIND, MODE>(a, s);

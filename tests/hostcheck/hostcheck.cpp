@@ -91,6 +91,32 @@ static void run_coop(int kind, int metric, int64_t b, const double* z1, const do
     }
     return;
   }
+  if (kind == kBounded) {
+    typedef coop::BoundedLayout<N> S;
+    std::vector<double> sm(S::kDoubles);
+    coop::HostExec ex{S::G};
+    const int per = 2 * N * N;
+    for (int64_t p = 0; p < b; ++p) {
+      for (auto& x : sm) x = -7.0e300;
+      if (grad)
+        coop::bounded_pair<N, true>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+      else
+        coop::bounded_pair<N, false>(ex, sm.data(), z1 + p * per, z2 + p * per, metric, w);
+      dist[p] = sm[S::DIST];
+      for (int k = 0; k < N; ++k) vvd[p * N + k] = sm[S::VS + k];
+      *status |= (unsigned)sm[S::FLAG];
+      if (grad)
+        for (int i = 0; i < N; ++i)
+          for (int j = 0; j < N; ++j) {
+            const int s = i * S::LD + j, t = j * S::LD + i, e = i * N + j;
+            g1[p * per + e] = 0.5 * (sm[S::G1R + s] + sm[S::G1R + t]);
+            g1[p * per + N * N + e] = 0.5 * (sm[S::G1I + s] + sm[S::G1I + t]);
+            g2[p * per + e] = 0.5 * (sm[S::G2R + s] + sm[S::G2R + t]);
+            g2[p * per + N * N + e] = 0.5 * (sm[S::G2I + s] + sm[S::G2I + t]);
+          }
+    }
+    return;
+  }
   const int per = 2 * N * N;
   std::vector<double> sm(L::kDoubles), smj(LJ::kDoubles);
   const int64_t cap = 3;  // scratch capacity in pairs; the slot rotates so that the indexing is exercised
@@ -150,7 +176,7 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
     return 1;
   }
   if (variant == 2 || variant == 3) {
-    if (kind == kBounded) return 1;
+    if (kind != kUpper && variant == 3) return 1;
     switch (n) {
 #define CASE(K)                                                                                  \
   case K:                                                                                        \

@@ -85,7 +85,7 @@ def test_status_flags(hostcheck):
     assert st & 1
 
 
-@pytest.mark.parametrize("path", golden_files("upper_n*.npz"), ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("path", golden_files("*_n*.npz"), ids=lambda p: p.split("/")[-1][:-4])
 def test_cooperative_templates_match_reference_golden(hostcheck, path):
     """namespace sympa::coop (the warp-cooperative shared-memory kernel, n >= 5 on the GPU) with the
     lanes of a group emulated one after the other; shared memory is poisoned before every pair."""
@@ -94,10 +94,11 @@ def test_cooperative_templates_match_reference_golden(hostcheck, path):
         w = r["wsum_w"] if m == "wsum" else None
         d, v, g1, g2, st = hostcheck(2, kind, n, m, r["z1"], r["z2"], w)
         assert st == 0
-        # the three-kernel split path (state parked in scratch) must give bit-identical results
-        ds, vs_, g1s, g2s, sts = hostcheck(3, kind, n, m, r["z1"], r["z2"], w)
-        assert sts == 0 and np.array_equal(ds, d) and np.array_equal(vs_, v)
-        assert np.array_equal(g1s, g1) and np.array_equal(g2s, g2)
+        if kind == "upper":
+            # the three-kernel split path (state parked in scratch) must give bit-identical results
+            ds, vs_, g1s, g2s, sts = hostcheck(3, kind, n, m, r["z1"], r["z2"], w)
+            assert sts == 0 and np.array_equal(ds, d) and np.array_equal(vs_, v)
+            assert np.array_equal(g1s, g1) and np.array_equal(g2s, g2)
         np.testing.assert_allclose(v, r["vvd"], rtol=VVD_RTOL, atol=VVD_ATOL)
         np.testing.assert_allclose(d, r["dist_" + m], rtol=VVD_RTOL)
         go = r["go"][:, None, None, None]
