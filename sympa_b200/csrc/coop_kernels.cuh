@@ -16,6 +16,76 @@ struct WarpExec {
   __device__ __forceinline__ int last() const { return active ? g + 1 : 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p && active) != 0; }
+
+  // Register-resident one-sided Jacobi, Brent-Luk ring ordering (see jacobi_ring_host for the schedule):
+  // each lane keeps a top and a bottom column in registers; after every round the top row moves one
+  // lane up and the bottom row one lane down with two warp shuffles per value.  Every lane of the
+  // warp executes the shuffles (inactive lanes carry garbage that nobody reads).
+  template <int N, bool IS_REAL>
+  __device__ __forceinline__ int jacobi(double* gr, double* gi, double*) const {
+    typedef coop::LayoutT<N, 2> L;
+    constexpr int NP = L::NP, LD = L::LD, G = L::G;
+    constexpr unsigned kFull = 0xffffffffu;
+    double tr[N], ti[N], br[N], bi[N];
+    int tid = 2 * g, bid = 2 * g + 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      tr[i] = gr[tid * LD + i];
+      ti[i] = IS_REAL ? 0.0 : gi[tid * LD + i];
+      br[i] = bid < N ? gr[bid * LD + i] : 0.0;
+      bi[i] = (bid < N && !IS_REAL) ? gi[bid * LD + i] : 0.0;
+    }
+    __syncwarp();
+    int sweep = 0;
+#pragma unroll 1
+    for (; sweep < kMaxSweeps; ++sweep) {
+      bool more = false;
+#pragma unroll 1
+      for (int r = 0; r < NP - 1; ++r) {
+        more = coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi) || more;
+        if (G > 1) {
+          const bool first = g == 0, last = g == G - 1;
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double up_r = __shfl_up_sync(kFull, first ? br[i] : tr[i], 1);
+            const double dn_r = __shfl_down_sync(kFull, br[i], 1);
+            const double old_t = tr[i];
+            tr[i] = first ? old_t : up_r;
+            br[i] = last ? old_t : dn_r;
+            if (!IS_REAL) {
+              const double up_i = __shfl_up_sync(kFull, first ? bi[i] : ti[i], 1);
+              const double dn_i = __shfl_down_sync(kFull, bi[i], 1);
+              const double old_ti = ti[i];
+              ti[i] = first ? old_ti : up_i;
+              bi[i] = last ? old_ti : dn_i;
+            }
+          }
+          const int up_id = __shfl_up_sync(kFull, first ? bid : tid, 1);
+          const int dn_id = __shfl_down_sync(kFull, bid, 1);
+          const int old_tid = tid;
+          tid = first ? old_tid : up_id;
+          bid = last ? old_tid : dn_id;
+        }
+      }
+      if (!any(more)) {
+        ++sweep;
+        break;
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (tid < N) gr[tid * LD + i] = tr[i];
+        if (bid < N) gr[bid * LD + i] = br[i];
+        if (!IS_REAL) {
+          if (tid < N) gi[tid * LD + i] = ti[i];
+          if (bid < N) gi[bid * LD + i] = bi[i];
+        }
+      }
+    }
+    __syncwarp();
+    return sweep;
+  }
 };
 
 template <int N>

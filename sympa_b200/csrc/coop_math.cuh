@@ -74,6 +74,9 @@ struct HostExec {
   int last() const { return G; }
   void sync() const {}
   bool any(bool p) const { return p; }
+  // Jacobi on the column-major matrix (gr, gi), column stride LD; defined after jacobi_ring_host
+  template <int N, bool IS_REAL>
+  int jacobi(double* gr, double* gi, double* conv) const;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -253,10 +256,136 @@ SY_HD void tournament(int r, int k, int* p, int* q) {
   loc::tournament_pair<N>(r, k, p, q);
 }
 
+// Orthogonalise one column pair held in registers (complex, or real when IS_REAL).  Returns true when
+// the pair was not yet converged (|g_p^H g_q|^2 > kStopRatio2 |g_p|^2 |g_q|^2).
+template <int N, bool IS_REAL>
+SY_HD bool rotate_columns(double* pr, double* pi, double* qr, double* qi) {
+  // two partial sums per quantity: shorter dependency chains
+  double al0 = 0.0, be0 = 0.0, cr0 = 0.0, ci0 = 0.0, al1 = 0.0, be1 = 0.0, cr1 = 0.0, ci1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    al0 += pr[i] * pr[i];
+    be0 += qr[i] * qr[i];
+    cr0 += pr[i] * qr[i];
+    if (!IS_REAL) {
+      al1 += pi[i] * pi[i];
+      be1 += qi[i] * qi[i];
+      cr1 += pi[i] * qi[i];
+      ci0 += pr[i] * qi[i];
+      ci1 += pi[i] * qr[i];
+    }
+  }
+  bool more = false;
+  double c, sr, si;
+  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, &c, &sr, &si, &more)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double a0 = pr[i], b0 = qr[i];
+      if (IS_REAL) {
+        pr[i] = c * a0 - sr * b0;
+        qr[i] = c * b0 + sr * a0;
+      } else {
+        const double a1 = pi[i], b1 = qi[i];
+        pr[i] = c * a0 - (sr * b0 + si * b1);
+        pi[i] = c * a1 - (sr * b1 - si * b0);
+        qr[i] = c * b0 + (sr * a0 - si * a1);
+        qi[i] = c * b1 + (sr * a1 + si * a0);
+      }
+    }
+  }
+  return more;
+}
+
+// Register-resident one-sided Jacobi in the Brent-Luk systolic ordering: lane g of a group holds a
+// "top" and a "bottom" column; every round each lane rotates its own pair, then the columns move
+// one lane along the ring (top row to the right, bottom row to the left, lane 0's top fixed), which
+// visits every pair once per NP - 1 rounds.  The columns never touch shared memory between the
+// initial load and the final store (the shared-memory version below moved both columns of every
+// pair through shared memory every round and was bound by bank-conflicted LDS/STS wavefronts).
+// An odd n gets a zero padding column, which no rotation ever changes.  Columns carry their index so
+// that they are stored back in place.  This is the host emulation (all lanes of the group in one
+// call); WarpExec implements the same schedule with warp shuffles.
+template <int N, bool IS_REAL>
+inline int jacobi_ring_host(int G, double* gr, double* gi) {
+  typedef LayoutT<N, 2> L;
+  constexpr int NP = L::NP, LD = L::LD;
+  double tr[L::G][N], ti[L::G][N], br[L::G][N], bi[L::G][N];
+  int tid[L::G], bid[L::G];
+  for (int g = 0; g < G; ++g) {
+    tid[g] = 2 * g;
+    bid[g] = 2 * g + 1;
+    for (int i = 0; i < N; ++i) {
+      tr[g][i] = gr[tid[g] * LD + i];
+      ti[g][i] = IS_REAL ? 0.0 : gi[tid[g] * LD + i];
+      br[g][i] = bid[g] < N ? gr[bid[g] * LD + i] : 0.0;
+      bi[g][i] = (bid[g] < N && !IS_REAL) ? gi[bid[g] * LD + i] : 0.0;
+    }
+  }
+  int sweep = 0;
+  for (; sweep < kMaxSweeps; ++sweep) {
+    bool more = false;
+    for (int r = 0; r < NP - 1; ++r) {
+      for (int g = 0; g < G; ++g) more = rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g]) || more;
+      if (G > 1) {
+        double ntr[L::G][N], nti[L::G][N], nbr[L::G][N], nbi[L::G][N];
+        int ntid[L::G], nbid[L::G];
+        for (int g = 0; g < G; ++g) {
+          // new top: lane 0 keeps its top, lane 1 takes lane 0's bottom, lane g takes lane g-1's top
+          const double* sr_ = g == 0 ? tr[0] : (g == 1 ? br[0] : tr[g - 1]);
+          const double* si_ = g == 0 ? ti[0] : (g == 1 ? bi[0] : ti[g - 1]);
+          ntid[g] = g == 0 ? tid[0] : (g == 1 ? bid[0] : tid[g - 1]);
+          // new bottom: lane g takes lane g+1's bottom, the last lane takes its own top
+          const double* ur_ = g == G - 1 ? tr[g] : br[g + 1];
+          const double* ui_ = g == G - 1 ? ti[g] : bi[g + 1];
+          nbid[g] = g == G - 1 ? tid[g] : bid[g + 1];
+          for (int i = 0; i < N; ++i) {
+            ntr[g][i] = sr_[i];
+            nti[g][i] = si_[i];
+            nbr[g][i] = ur_[i];
+            nbi[g][i] = ui_[i];
+          }
+        }
+        for (int g = 0; g < G; ++g) {
+          tid[g] = ntid[g];
+          bid[g] = nbid[g];
+          for (int i = 0; i < N; ++i) {
+            tr[g][i] = ntr[g][i];
+            ti[g][i] = nti[g][i];
+            br[g][i] = nbr[g][i];
+            bi[g][i] = nbi[g][i];
+          }
+        }
+      }
+    }
+    if (!more) {
+      ++sweep;
+      break;
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    for (int i = 0; i < N; ++i) {
+      if (tid[g] < N) gr[tid[g] * LD + i] = tr[g][i];
+      if (bid[g] < N) gr[bid[g] * LD + i] = br[g][i];
+      if (!IS_REAL) {
+        if (tid[g] < N) gi[tid[g] * LD + i] = ti[g][i];
+        if (bid[g] < N) gi[bid[g] * LD + i] = bi[g][i];
+      }
+    }
+  }
+  return sweep;
+}
+
 // One-sided Jacobi on the column-major complex matrix (gr, gi) in shared memory, column stride LD
 // (no V).  `conv` holds 2 * G not-converged flags, double-buffered by sweep parity.
+template <int N, bool IS_REAL>
+int HostExec::jacobi(double* gr, double* gi, double*) const {
+  return jacobi_ring_host<N, IS_REAL>(G, gr, gi);
+}
+
+// The first implementation, kept for reference: same mathematics with the columns living in shared
+// memory and a tournament pairing (one pair per lane per round, __syncwarp between rounds).
 template <int N, bool IS_REAL, class Ex>
-SY_HD int jacobi(Ex& ex, double* gr, double* gi, double* conv) {
+SY_HD int jacobi_smem(Ex& ex, double* gr, double* gi, double* conv) {
   constexpr int NP = Layout<N>::NP;
   constexpr int G = Layout<N>::G;
   constexpr int LD = Layout<N>::LD;
@@ -499,7 +628,7 @@ SY_HD void spectrum(Ex& ex, double* sm, int metric, const double* wsum_w) {
   constexpr int LD = LT::LD;
   double* gr = sm + LT::GR;
   double* gi = sm + LT::GI;
-  const int sweeps = jacobi<N, false>(ex, gr, gi, sm + LT::WORST);
+  const int sweeps = ex.template jacobi<N, false>(gr, gi, sm + LT::WORST);
   SY_STAGE_BEGIN(ex)
   for (int k = g; k < N; k += G) {
     double s0 = 0.0, s1 = 0.0;
@@ -968,7 +1097,7 @@ SY_HD void spd_pair(Ex& ex, double* sm, const double* p1, const double* p2) {
     gj[c * LD + r] = gm[r * LD + c];  // column-major copy for the Jacobi
   }
   SY_STAGE_END(ex)
-  const int sweeps = jacobi<N, true>(ex, gj, gj, sm + L::WORST);
+  const int sweeps = ex.template jacobi<N, true>(gj, gj, sm + L::WORST);
   SY_STAGE_BEGIN(ex)
   for (int k = g; k < N; k += G) {
     double s0 = 0.0;
