@@ -222,6 +222,31 @@ __global__ void __launch_bounds__(32) coop_kernel(const PairArgs a) {
         p2 = a.z2 + p * PER;
       }
     }
+    // L2 prefetch of the rows of this lane's NEXT pair (the table gather is a dependent chain
+    // idx -> row address -> data whose latency is exposed at one warp per scheduler)
+    {
+      const int64_t pn = p + stride;
+      if (slot < PW && pn < a.num_pairs) {
+        const double* q1;
+        const double* q2;
+        bool okn = true;
+        if (a.idx != nullptr) {
+          const int64_t j1 = __ldg(a.idx + 2 * pn), j2 = __ldg(a.idx + 2 * pn + 1);
+          okn = j1 >= 0 && j1 < a.num_rows && j2 >= 0 && j2 < a.num_rows;
+          q1 = a.table + (okn ? j1 : 0) * PER;
+          q2 = a.table + (okn ? j2 : 0) * PER;
+        } else {
+          q1 = a.z1 + pn * PER;
+          q2 = a.z2 + pn * PER;
+        }
+        if (okn) {
+          for (int off = g * 16; off < PER; off += G * 16) {  // one 128-byte line per step
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q2 + off));
+          }
+        }
+      }
+    }
     WarpExec ex{g, active};
     if (KIND == kSpd)
       coop::spd_pair<N, GRAD>(ex, sm, p1, p2);

@@ -214,6 +214,30 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
       p1 = a.z1 + p * PER;
       p2 = a.z2 + p * PER;
     }
+    {  // L2 prefetch of the rows of this thread's next pair
+      const int64_t pn = base + stride + threadIdx.x;
+      if (pn < a.num_pairs) {
+        const double* q1;
+        const double* q2;
+        bool okn = true;
+        if (a.idx != nullptr) {
+          const longlong2 jn = __ldg(reinterpret_cast<const longlong2*>(a.idx) + pn);
+          okn = jn.x >= 0 && jn.x < a.num_rows && jn.y >= 0 && jn.y < a.num_rows;
+          q1 = a.table + (okn ? jn.x : 0) * PER;
+          q2 = a.table + (okn ? jn.y : 0) * PER;
+        } else {
+          q1 = a.z1 + pn * PER;
+          q2 = a.z2 + pn * PER;
+        }
+        if (okn) {
+#pragma unroll
+          for (int off = 0; off < PER; off += 16) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q2 + off));
+          }
+        }
+      }
+    }
     double vs[N];
     double dist;
     unsigned stp = 0;  // status of this pair; dropped when the thread only recomputes a stand-in pair
