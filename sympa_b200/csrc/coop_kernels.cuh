@@ -37,12 +37,13 @@ struct WarpExec {
     }
     __syncwarp();
     int sweep = 0;
+    bool done = !active;  // this pair's group has converged: its columns are frozen from here on
 #pragma unroll 1
     for (; sweep < kMaxSweeps; ++sweep) {
-      bool more = false;
+      unsigned conv = 0u;
 #pragma unroll 1
       for (int r = 0; r < NP - 1; ++r) {
-        more = coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi) || more;
+        if (!done) conv |= coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi);
         if (G > 1) {
           const bool first = g == 0, last = g == G - 1;
 #pragma unroll
@@ -67,7 +68,15 @@ struct WarpExec {
           bid = last ? old_tid : dn_id;
         }
       }
-      if (!any(more)) {
+      // the flags are combined over the lanes of THIS pair's group only: a pair's sweep count, and
+      // therefore its result, does not depend on which other pairs share the warp.  The loop runs
+      // until every group of the warp is done; converged groups keep shuffling (the ring must stay
+      // in step) but no longer rotate.
+      unsigned gconv = 0u;
+#pragma unroll
+      for (int k = 0; k < G; ++k) gconv |= __shfl_sync(kFull, conv, (threadIdx.x & 31) - g + k);
+      done = done || loc::jacobi_sweep_is_last(gconv);
+      if (__all_sync(kFull, done)) {
         ++sweep;
         break;
       }

@@ -89,7 +89,11 @@ SY_HD void mm_cols(const double* a, const double* b, int j0, int j1, double* acc
   constexpr int LD = Layout<N>::LD;
   const bool two = j1 < N;
   const int jj1 = two ? j1 : j0;
-#pragma unroll 1
+#ifndef SY_MM_UNROLL
+#define SY_MM_UNROLL 2
+#endif
+  constexpr int kMmUnroll = SY_MM_UNROLL;
+#pragma unroll kMmUnroll
   for (int k = 0; k < N; ++k) {
     const double b0 = TB ? b[j0 * LD + k] : b[k * LD + j0];
     double b1 = TB ? b[jj1 * LD + k] : b[k * LD + jj1];
@@ -256,10 +260,10 @@ SY_HD void tournament(int r, int k, int* p, int* q) {
   loc::tournament_pair<N>(r, k, p, q);
 }
 
-// Orthogonalise one column pair held in registers (complex, or real when IS_REAL).  Returns true when
-// the pair was not yet converged (|g_p^H g_q|^2 > kStopRatio2 |g_p|^2 |g_q|^2).
+// Orthogonalise one column pair held in registers (complex, or real when IS_REAL).  Returns the
+// convergence flags of the pair (kConvLoose | kConvStrict | kConvClose, see jacobi_rotation).
 template <int N, bool IS_REAL>
-SY_HD bool rotate_columns(double* pr, double* pi, double* qr, double* qi) {
+SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi) {
   // two partial sums per quantity: shorter dependency chains
   double al0 = 0.0, be0 = 0.0, cr0 = 0.0, ci0 = 0.0, al1 = 0.0, be1 = 0.0, cr1 = 0.0, ci1 = 0.0;
 #pragma unroll
@@ -275,9 +279,9 @@ SY_HD bool rotate_columns(double* pr, double* pi, double* qr, double* qi) {
       ci1 += pi[i] * qr[i];
     }
   }
-  bool more = false;
+  unsigned conv = 0u;
   double c, sr, si;
-  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, &c, &sr, &si, &more)) {
+  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, &c, &sr, &si, &conv)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double a0 = pr[i], b0 = qr[i];
@@ -293,7 +297,7 @@ SY_HD bool rotate_columns(double* pr, double* pi, double* qr, double* qi) {
       }
     }
   }
-  return more;
+  return conv;
 }
 
 // Register-resident one-sided Jacobi in the Brent-Luk systolic ordering: lane g of a group holds a
@@ -323,9 +327,9 @@ inline int jacobi_ring_host(int G, double* gr, double* gi) {
   }
   int sweep = 0;
   for (; sweep < kMaxSweeps; ++sweep) {
-    bool more = false;
+    unsigned conv = 0u;
     for (int r = 0; r < NP - 1; ++r) {
-      for (int g = 0; g < G; ++g) more = rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g]) || more;
+      for (int g = 0; g < G; ++g) conv |= rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g]);
       if (G > 1) {
         double ntr[L::G][N], nti[L::G][N], nbr[L::G][N], nbi[L::G][N];
         int ntid[L::G], nbid[L::G];
@@ -357,7 +361,7 @@ inline int jacobi_ring_host(int G, double* gr, double* gi) {
         }
       }
     }
-    if (!more) {
+    if (loc::jacobi_sweep_is_last(conv)) {
       ++sweep;
       break;
     }
@@ -422,9 +426,9 @@ SY_HD int jacobi_smem(Ex& ex, double* gr, double* gi, double* conv) {
           ci1 += pi[i] * qr[i];
         }
         const double al = al0 + al1, be = be0 + be1, cr = cr0 + cr1, ci = ci0 - ci1;
-        bool more = false;
+        unsigned conv = 0u;
         double c, sr, si;
-        if (loc::jacobi_rotation(al, be, cr, ci, &c, &sr, &si, &more)) {
+        if (loc::jacobi_rotation(al, be, cr, ci, &c, &sr, &si, &conv)) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             gr[p * LD + i] = c * pr[i] - (sr * qr[i] + si * qi[i]);
@@ -435,7 +439,7 @@ SY_HD int jacobi_smem(Ex& ex, double* gr, double* gi, double* conv) {
             }
           }
         }
-        notconv = more ? 1.0 : 0.0;
+        notconv = (conv & loc::kConvLoose) ? 1.0 : 0.0;
       }
       wbuf[g] = (r == 0) ? notconv : (notconv > wbuf[g] ? notconv : wbuf[g]);
       SY_STAGE_END(ex)

@@ -375,3 +375,36 @@ def test_training_with_fused_optimizer_equals_host_optimizer(sb):
     np.testing.assert_allclose(res[True][0], res[False][0], rtol=1e-8)
     torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-7, atol=1e-10)
     assert res[True][0][-1] < res[True][0][0]      # it trains
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 10])
+def test_far_apart_and_nearly_coincident_pairs(sb, n):
+    """the clamp of siegel_manifold.py:69 (1 - d < eps, points very far apart: clustered singular values
+    with derivative weights spanning orders of magnitude) and nearly coincident points (d ~ 1e-9)"""
+    g = torch.Generator().manual_seed(77)
+    base = so.upper_spread(6, n, generator=g, scale=0.2)
+    far = base.clone()
+    sc = torch.tensor([1e5, 3e5, 1e6, 1e7, 4e5, 2e6]).sqrt().reshape(-1, 1) * (1.0 + 0.3 * torch.arange(n)).reshape(1, -1)
+    far[:, 1] = sc.unsqueeze(-1) * far[:, 1] * sc.unsqueeze(-2)
+    near = base.clone()
+    near[:, 0] = near[:, 0] + 1e-9 * so.sym(torch.randn(6, n, n, dtype=torch.float64, generator=g))
+    near[:, 1] = near[:, 1] * (1 + 1e-9)
+    for metric in ("riem", "fone"):
+        man = make_manifold(sb, "upper", n, metric)
+        d_ref, g1_ref, g2_ref, _ = so.dist_and_grads("upper", base, far, metric)
+        a1, a2 = base.clone().cuda().requires_grad_(True), far.clone().cuda().requires_grad_(True)
+        d = man.dist(a1, a2)
+        d.sum().backward()
+        np.testing.assert_allclose(d.detach().cpu().numpy(), d_ref.numpy(), rtol=1e-7)
+        tol = 1e-6 if n <= 6 else 1e-5
+        for b in range(6):
+            for got, ref in ((a1.grad[b], g1_ref[b]), (a2.grad[b], g2_ref[b])):
+                ref = 0.5 * (ref + ref.transpose(-1, -2))
+                assert (got.cpu() - ref).abs().max() <= tol * ref.abs().max()
+        d_ref = so.dist("upper", base, near, metric)
+        a1 = base.clone().cuda().requires_grad_(True)
+        d = man.dist(a1, near.cuda())
+        d.sum().backward()
+        np.testing.assert_allclose(d.detach().cpu().numpy(), d_ref.numpy(), rtol=1e-4, atol=1e-13)
+        assert torch.isfinite(a1.grad).all()
+    sb.ops.check_status()
