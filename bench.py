@@ -22,8 +22,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+    # keep NCCL's version banner (printed to STDOUT at VERSION and WARN level) out of the way: rank 0 prints
+    # ONE JSON line.  An unrecognised level means "no logging" to NCCL; INFO / TRACE set by the user are kept.
+    os.environ["NCCL_DEBUG"] = "NONE"
 
 import torch  # noqa: E402
 
