@@ -30,6 +30,12 @@ if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
 import torch  # noqa: E402
 
 
+def default_pairs(n):
+    """pairs per GPU per step: BASELINE.json's 64M-pair batch over 8 GPUs (2^23 per GPU) where the saved unit
+    gradients fit comfortably, smaller for the large matrix sizes (a step is still >= 25 ms there)."""
+    return (1 << 23) if n <= 4 else ((1 << 20) if n <= 6 else (1 << 18))
+
+
 def algorithmic_bytes_per_pair(kind, n):
     """read two rows, accumulate two gradient rows, two int64 indices, vvd out, dist
     out, upstream gradient in."""
@@ -163,7 +169,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     kind, n = args.kind, args.n
     rows = args.rows
-    b = args.pairs if args.pairs else ((1 << 22) if n <= 4 else (1 << 19 if n <= 6 else 1 << 16))
+    b = args.pairs if args.pairs else default_pairs(n)
     if kind == "spd":
         man = SymmetricPositiveDefinite().to(dev)
     else:
@@ -480,7 +486,7 @@ def run_reference(args):
         step()
     el = time.perf_counter() - t0
     value = b * args.steps / el
-    cfg_b = args.pairs if args.pairs else ((1 << 22) if n <= 4 else (1 << 19 if n <= 6 else 1 << 16))
+    cfg_b = args.pairs if args.pairs else default_pairs(n)
     out = {
         "impl": "reference", "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / args.steps * 1e3,
