@@ -170,7 +170,7 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
   if (variant == 0) {
     switch (n) {
 #define CASE(K) case K: run_reg<K>(kind, metric, b, z1, z2, w, grad, dist, vvd, g1, g2, status); return 0;
-      CASE(1) CASE(2) CASE(3) CASE(4)
+      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6)
 #undef CASE
     }
     return 1;
@@ -238,7 +238,7 @@ extern "C" int64_t hostcheck_rsgd(int variant, int kind, int n, int64_t rows, do
   if (variant == 0) {
     switch (n) {
 #define CASE(K) case K: return rsgd_reg<K>(kind, rows, table, grad, lr);
-      CASE(1) CASE(2) CASE(3) CASE(4)
+      CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6)
 #undef CASE
     }
     return -1;

@@ -16,7 +16,7 @@ VVD_ATOL = 1e-12
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
 def test_templates_match_reference_golden(hostcheck, path):
     kind, n, regime, r = load_golden(path)
-    variants = (0, 1) if n <= 4 else (1,)
+    variants = (0, 1) if n <= 6 else (1,)
     for variant in variants:
         for m in METRICS:
             w = r["wsum_w"] if m == "wsum" else None
@@ -38,7 +38,7 @@ def test_spd_against_oracle(hostcheck, n):
     x, y = so.spd_spread(16, n, generator=g), so.spd_spread(16, n, generator=g)
     go = torch.rand(16, generator=g, dtype=torch.float64) + 0.5
     d, g1, g2, _ = so.dist_and_grads("spd", x, y, grad_out=go)
-    for variant in ((0, 1, 2) if n <= 4 else (1, 2)):     # 2 = cooperative kernel templates
+    for variant in ((0, 1, 2) if n <= 6 else (1, 2)):     # 2 = cooperative kernel templates
         dd, vv, h1, h2, st = hostcheck(variant, "spd", n, "riem", x.numpy(), y.numpy())
         assert st == 0
         np.testing.assert_allclose(dd, d.numpy(), rtol=1e-9)
@@ -127,7 +127,7 @@ def _extreme_pairs(n):
 @pytest.mark.parametrize("n", [2, 3, 4, 6])
 def test_clamped_and_nearly_coincident_pairs(hostcheck, n):
     base, far, near = _extreme_pairs(n)
-    variants = (0, 2) if n <= 4 else (1, 2)
+    variants = (0, 2) if n <= 6 else (1, 2)
     for metric in ("riem", "fone", "finf"):
         for other, name in ((far, "far"), (near, "near")):
             if name == "far" and metric == "finf":

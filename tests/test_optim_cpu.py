@@ -72,7 +72,7 @@ def test_row_update_templates_match_oracle_upper(hostcheck, n, lr):
     table, grad, touched = make("upper", 40, n, 11 + n)
     ref = so.rsgd_step("upper", table, grad, lr)
     moved_ref = int((~torch.all(torch.linalg.eigvalsh((table - lr * so.upper_egrad2rgrad(table, grad))[:, 1]) > 1e-5, dim=-1)).sum())
-    for variant in ((0, 1) if n <= 4 else (1,)):
+    for variant in ((0, 1) if n <= 6 else (1,)):
         out, projected = hostcheck.rsgd(variant, "upper", n, table.numpy(), grad.numpy(), lr)
         torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-9, atol=1e-11)
         assert projected == moved_ref
@@ -89,6 +89,6 @@ def test_row_update_templates_match_oracle_spd(hostcheck, n):
     lr = 0.05
     u = -lr * (x @ gr @ x)
     ref = so.sym(x + u + 0.5 * u @ torch.linalg.solve(x, u))
-    for variant in ((0, 1) if n <= 4 else (1,)):
+    for variant in ((0, 1) if n <= 6 else (1,)):
         out, _ = hostcheck.rsgd(variant, "spd", n, x.numpy(), gr.numpy(), lr)
         torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-11, atol=1e-13)

@@ -51,7 +51,9 @@ def test_manifold_dist_matches_reference_golden(sb, path):
             np.testing.assert_allclose(man.metric.weights.grad.cpu().numpy(), r["gw_wsum"], rtol=1e-9)
         with torch.no_grad():
             d0 = man.dist(z1, z2)
-        assert torch.equal(d0, d.detach())      # forward-only kernel == forward+grad kernel
+        # forward-only kernel vs forward+grad kernel: two instantiations of the same templates, equal up
+        # to the compiler's FMA contraction choices
+        torch.testing.assert_close(d0, d.detach(), rtol=1e-13, atol=1e-15)
     sb.ops.check_status()
 
 
@@ -219,10 +221,10 @@ def test_full_size_properties(sb, kind, n):
     sb.ops.check_status()
 
 
-@pytest.mark.parametrize("n", [5, 6, 10])
+@pytest.mark.parametrize("n", [7, 8, 10])
 @pytest.mark.parametrize("metric", ["riem", "wsum"])
 def test_split_path_equals_single_kernel_path(sb, n, metric):
-    """upper, n > 4: the three-kernel path (state parked in scratch; used when the batch is large enough
+    """upper, n > 6 (the cooperative kernels): the three-kernel path (state parked in scratch; used when the batch is large enough
     and scratch is given) must reproduce the single-kernel path bit for bit - forward, saved unit
     gradients and the fused distortion step."""
     from sympa_b200 import _lib
