@@ -79,6 +79,10 @@ struct HostExec {
   int jacobi(double* gr, double* gi, double* conv) const;
 };
 
+#ifndef SY_MM_UNROLL
+#define SY_MM_UNROLL 2
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // All shared-memory matrices are n x n with leading dimension LD = Layout<N>::LD.
 // dense helper: accumulate the two owned columns j0 = g, j1 = g + G (j1 may be >= N: ignored)
@@ -89,9 +93,6 @@ SY_HD void mm_cols(const double* a, const double* b, int j0, int j1, double* acc
   constexpr int LD = Layout<N>::LD;
   const bool two = j1 < N;
   const int jj1 = two ? j1 : j0;
-#ifndef SY_MM_UNROLL
-#define SY_MM_UNROLL 2
-#endif
   constexpr int kMmUnroll = SY_MM_UNROLL;
 #pragma unroll kMmUnroll
   for (int k = 0; k < N; ++k) {
@@ -103,6 +104,32 @@ SY_HD void mm_cols(const double* a, const double* b, int j0, int j1, double* acc
       const double av = TA ? a[k * LD + i] : a[i * LD + k];
       acc0[i] += av * b0;
       acc1[i] += av * b1;
+    }
+  }
+}
+
+// two products that share the left operand: (A op) Bx and (A op) By for the owned columns; the column
+// of A is read from shared memory once per k for four accumulator columns
+template <int N, bool TA>
+SY_HD void mm_cols2(const double* a, const double* bx, const double* by, int j0, int j1, double* x0, double* x1,
+                    double* y0, double* y1) {
+  constexpr int LD = Layout<N>::LD;
+  const bool two = j1 < N;
+  const int jj1 = two ? j1 : j0;
+  constexpr int kMmUnroll = SY_MM_UNROLL;
+#pragma unroll kMmUnroll
+  for (int k = 0; k < N; ++k) {
+    const double bx0 = bx[k * LD + j0], by0 = by[k * LD + j0];
+    double bx1 = bx[k * LD + jj1], by1 = by[k * LD + jj1];
+    bx1 = two ? bx1 : 0.0;
+    by1 = two ? by1 : 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double av = TA ? a[k * LD + i] : a[i * LD + k];
+      x0[i] += av * bx0;
+      x1[i] += av * bx1;
+      y0[i] += av * by0;
+      y1[i] += av * by1;
     }
   }
 }
@@ -597,8 +624,12 @@ SY_HD void upper_prologue(Ex& ex, double* sm, const In& in) {
   chol_inv<N>(ex, a1, a3, li, rd, flag);  // li = chol(Y1)^-1, scratch a3
 
   SY_STAGE_BEGIN(ex)
-  mm_stage<N, false, false>(li, a0, a1, g, 1.0, 0.0);  // a1 = li D
-  mm_stage<N, false, false>(li, a2, a3, g, 1.0, 0.0);  // a3 = li Y2
+  double x0[N], x1[N], y0[N], y1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  mm_cols2<N, false>(li, a0, a2, g, g + G, x0, x1, y0, y1);
+  put_cols<N>(a1, g, g + G, x0, x1, 1.0, 0.0);  // a1 = li D
+  put_cols<N>(a3, g, g + G, y0, y1, 1.0, 0.0);  // a3 = li Y2
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
   mm_stage<N, false, true>(a1, li, a0, g, -1.0, 0.0);  // a0 = -A = -(li D) li^T
@@ -697,13 +728,11 @@ SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   double x0[N], x1[N], y0[N], y1[N];
   zero2<N>(x0, x1);
   zero2<N>(y0, y1);
-  mm_cols<N, false, false>(a3, Q, j0, j1, x0, x1);  // Fr Q
-  mm_cols<N, false, false>(a3, P, j0, j1, y0, y1);  // Fr P
+  mm_cols2<N, false>(a3, Q, P, j0, j1, x0, x1, y0, y1);  // Fr Q, Fr P
   double z0[N], z1[N], w0[N], w1[N];
   zero2<N>(z0, z1);
   zero2<N>(w0, w1);
-  mm_cols<N, false, false>(a5, P, j0, j1, z0, z1);  // Fi P
-  mm_cols<N, false, false>(a5, Q, j0, j1, w0, w1);  // Fi Q
+  mm_cols2<N, false>(a5, P, Q, j0, j1, z0, z1, w0, w1);  // Fi P, Fi Q
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     a1[i * LD + j0] = a3[i * LD + j0] - 2.0 * (x0[i] - z0[i]);
@@ -732,10 +761,8 @@ SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   zero2<N>(y0, y1);
   zero2<N>(z0, z1);
   zero2<N>(w0, w1);
-  mm_cols<N, false, false>(P, a3, j0, j1, x0, x1);
-  mm_cols<N, false, false>(Q, a5, j0, j1, y0, y1);
-  mm_cols<N, false, false>(P, a5, j0, j1, z0, z1);
-  mm_cols<N, false, false>(Q, a3, j0, j1, w0, w1);
+  mm_cols2<N, false>(P, a3, a5, j0, j1, x0, x1, z0, z1);  // P GNr, P GNi
+  mm_cols2<N, false>(Q, a5, a3, j0, j1, y0, y1, w0, w1);  // Q GNi, Q GNr
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     a1[i * LD + j0] = x0[i] - y0[i];
@@ -755,10 +782,8 @@ SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   zero2<N>(y0, y1);
   zero2<N>(z0, z1);
   zero2<N>(w0, w1);
-  mm_cols<N, false, false>(a1, P, j0, j1, x0, x1);
-  mm_cols<N, false, false>(a2, Q, j0, j1, y0, y1);
-  mm_cols<N, false, false>(a1, Q, j0, j1, z0, z1);
-  mm_cols<N, false, false>(a2, P, j0, j1, w0, w1);
+  mm_cols2<N, false>(a1, P, Q, j0, j1, x0, x1, z0, z1);  // Tmr P, Tmr Q
+  mm_cols2<N, false>(a2, Q, P, j0, j1, y0, y1, w0, w1);  // Tmi Q, Tmi P
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     a3[i * LD + j0] = -(x0[i] - y0[i]);
@@ -779,8 +804,12 @@ SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   }
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
-  mm_stage<N, false, false>(li, a0, a1, g, 1.0, 0.0);  // a1 = T1 = li D
-  mm_stage<N, false, false>(li, a4, a2, g, 1.0, 0.0);  // a2 = T2 = li Y2
+  double x0[N], x1[N], y0[N], y1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  mm_cols2<N, false>(li, a0, a4, g, g + G, x0, x1, y0, y1);
+  put_cols<N>(a1, g, g + G, x0, x1, 1.0, 0.0);  // a1 = T1 = li D
+  put_cols<N>(a2, g, g + G, y0, y1, 1.0, 0.0);  // a2 = T2 = li Y2
   SY_STAGE_END(ex)
   // ---- a0 = G_Li = 2 (G_A T1 + G_B T2)   (only its lower triangle is used)
   SY_STAGE_BEGIN(ex)
@@ -817,8 +846,12 @@ SY_HD void upper_backward(Ex& ex, double* sm, const In& in) {
   mm_stage<N, false, false>(a5, li, a2, g, 1.0, 0.0);  // a2 = G_B li
   SY_STAGE_END(ex)
   SY_STAGE_BEGIN(ex)
-  mm_stage<N, true, false>(li, a1, a4, g, 1.0, 0.0);  // a4 = G_X2 = li^T G_A li
-  mm_stage<N, true, false>(li, a2, a3, g, 1.0, 0.0);  // a3 = G_Y2 = li^T G_B li
+  double x0[N], x1[N], y0[N], y1[N];
+  zero2<N>(x0, x1);
+  zero2<N>(y0, y1);
+  mm_cols2<N, true>(li, a1, a2, g, g + G, x0, x1, y0, y1);
+  put_cols<N>(a4, g, g + G, x0, x1, 1.0, 0.0);  // a4 = G_X2 = li^T G_A li
+  put_cols<N>(a3, g, g + G, y0, y1, 1.0, 0.0);  // a3 = G_Y2 = li^T G_B li
   SY_STAGE_END(ex)
 }
 
