@@ -23,10 +23,18 @@
 namespace sympa {
 namespace coop {
 
+// leading dimension of the shared-memory matrices: n + 1 for even n (odd: conflict-free column
+// walks).  The unpadded n fits one more CTA per SM at n = 10 (6 instead of 5) but measured the same
+// on the B200 (23.0 vs 23.5 ms per 2^20 pairs at n = 10, 11.2 vs 11.0 ms at n = 8): the cooperative
+// kernel is bound by its serial stage structure, not by occupancy.
+#ifndef SY_COOP_LD
+#define SY_COOP_LD(N) (((N) % 2 == 0) ? (N) + 1 : (N))
+#endif
+
 template <int N, int NBUF>
 struct LayoutT {
   static constexpr int NN = N * N;
-  static constexpr int LD = (N % 2 == 0) ? N + 1 : N;  // odd leading dimension: no systematic bank conflicts
+  static constexpr int LD = SY_COOP_LD(N);
   static constexpr int BUF = N * LD;                    // one n x n buffer
   static constexpr int NP = (N % 2 == 0) ? N : N + 1;  // padded column count for the tournament
   static constexpr int G = NP / 2;                      // lanes per pair
