@@ -315,8 +315,8 @@ SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi) {
     }
   }
   unsigned conv = 0u;
-  double c, sr, si;
-  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, &c, &sr, &si, &conv)) {
+  double c, sr, si, xf;
+  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, loc::jacobi_stop_ratio2<N>(), &c, &sr, &si, &xf, &conv)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double a0 = pr[i], b0 = qr[i];
@@ -462,8 +462,8 @@ SY_HD int jacobi_smem(Ex& ex, double* gr, double* gi, double* conv) {
         }
         const double al = al0 + al1, be = be0 + be1, cr = cr0 + cr1, ci = ci0 - ci1;
         unsigned conv = 0u;
-        double c, sr, si;
-        if (loc::jacobi_rotation(al, be, cr, ci, &c, &sr, &si, &conv)) {
+        double c, sr, si, xf;
+        if (loc::jacobi_rotation(al, be, cr, ci, loc::jacobi_stop_ratio2<N>(), &c, &sr, &si, &xf, &conv)) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             gr[p * LD + i] = c * pr[i] - (sr * qr[i] + si * qi[i]);

@@ -88,6 +88,9 @@ constexpr int kThreads = SY_PAIR_THREADS;
 #ifndef SY_REG_MIN_BLOCKS
 #define SY_REG_MIN_BLOCKS 2
 #endif
+#ifndef SY_REG_MIN_BLOCKS_3
+#define SY_REG_MIN_BLOCKS_3 SY_REG_MIN_BLOCKS
+#endif
 
 // namespace switch: reg = unrolled / registers (N <= SY_REG_MAX_N), loc = rolled / local memory
 template <bool REG>
@@ -166,6 +169,139 @@ __device__ __forceinline__ void atomic_add_full(double* __restrict__ out, const 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory staging of the gather and of the saved unit gradients (register kernels, n = 2..4).
+//
+// One pair per thread means that a per-thread row fetch touches 32 different lines per warp
+// instruction (32 LDG.128 x 32 lines per pair and warp, the same again for the stores), and that the
+// dependent index -> row loads sit at the head of every pair with two warps per scheduler to hide
+// them: ncu attributed 19 % of the warp stall samples of pair_kernel<4> to long_scoreboard on the
+// first use of the rows and 7 % to lg_throttle on the stores.  Instead, each warp copies the rows of
+// its NEXT 32 pairs into shared memory with cp.async (16-byte chunks, consecutive lanes on
+// consecutive chunks of a row, so an instruction touches 2-4 lines) while it computes the current
+// ones, and it writes the saved unit gradients through shared memory as contiguous 512-byte
+// segments (the state of 32 consecutive pairs is contiguous in HBM).  Indices are staged the same
+// way two iterations ahead.  Slot strides are an odd number of 16-byte chunks: conflict-free
+// LDS.128 / STS.128 when every lane walks its own slot.
+#ifndef SY_STAGE_MIN_N
+#define SY_STAGE_MIN_N 3
+#endif
+#ifndef SY_STAGE_MAX_N
+#define SY_STAGE_MAX_N 4
+#endif
+
+template <int N, int KIND>
+struct StageCfg {
+  static constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;  // doubles per point
+  // (spd at n = 4 runs 3 CTAs/SM at 160 registers and measured slower with the staging: left per-thread)
+  static constexpr bool kOn = (N >= SY_STAGE_MIN_N) && (N <= SY_STAGE_MAX_N) && (N <= SY_REG_MAX_N) && (PER % 2 == 0) &&
+                              (KIND != kSpd);
+  static constexpr int RC = PER / 2;                           // 16-byte chunks per point
+  static constexpr int IN_STRIDE = 2 * RC + 1;                 // chunks per pair slot (two points + pad)
+  static constexpr int OUT_STRIDE = (RC % 2 == 0) ? RC + 1 : RC;
+  static constexpr int IN_BYTES = 32 * IN_STRIDE * 16;
+  static constexpr int OUT_BYTES = 32 * OUT_STRIDE * 16;
+  static constexpr int IDX_BYTES = 2 * 32 * 16;                // two generations of 32 index pairs
+  // per-warp layout: [rows in][indices][unit gradients out - only the forward+save kernel has them]
+  __host__ __device__ static constexpr int warp_bytes(int mode) { return IN_BYTES + IDX_BYTES + (mode == 1 ? OUT_BYTES : 0); }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// index pairs of the warp's 32 pairs starting at pair w0 -> idxb[0..31] (asynchronous).  Pairs past the
+// end are clamped to the last one: every warp of a CTA that still has work computes on valid data.
+__device__ __forceinline__ void stage_indices(const PairArgs& a, int64_t w0, longlong2* idxb, int lane) {
+  if (a.idx == nullptr) return;
+  int64_t p = w0 + lane;
+  p = p < a.num_pairs ? p : a.num_pairs - 1;
+  cp_async16(idxb + lane, reinterpret_cast<const longlong2*>(a.idx) + p);
+}
+
+// Owner lanes check the (landed) index pairs of a generation once, replace rejected ones by (0, 0) in
+// place so that stage_rows can use them blindly, and return the warp's reject mask.
+__device__ __forceinline__ unsigned validate_indices(const PairArgs& a, longlong2* idxb, int lane) {
+  if (a.idx == nullptr) return 0u;
+  const longlong2 ij = idxb[lane];
+  const bool bad = ij.x < 0 || ij.x >= a.num_rows || ij.y < 0 || ij.y >= a.num_rows;
+  if (bad) idxb[lane] = make_longlong2(0, 0);
+  const unsigned m = __ballot_sync(0xffffffffu, bad);
+  __syncwarp();
+  return m;
+}
+
+// rows of the warp's 32 pairs starting at pair w0 -> in[] (asynchronous).  idxb holds their
+// (already landed and validated) index pairs; the tail is clamped to the last pair.
+template <int N, int KIND>
+__device__ __forceinline__ void stage_rows(const PairArgs& a, int64_t w0, const longlong2* idxb, unsigned char* in,
+                                           int lane) {
+  using S = StageCfg<N, KIND>;
+  // flat chunk f = it * 32 + lane among the warp's 32 pairs: pair j = f / (2 RC), then the point
+  // (side 0 / 1) and the chunk c within the point
+  if (a.idx != nullptr) {
+    const int64_t* rows = reinterpret_cast<const int64_t*>(idxb);  // validated by validate_indices
+#pragma unroll
+    for (int it = 0; it < 2 * S::RC; ++it) {
+      const int f = it * 32 + lane;
+      const int j = f / (2 * S::RC);
+      const int rem = f - j * (2 * S::RC);
+      const int side = rem / S::RC;
+      const int c = rem - side * S::RC;
+      cp_async16(in + (j * S::IN_STRIDE + rem) * 16, a.table + rows[2 * j + side] * S::PER + 2 * c);
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < 2 * S::RC; ++it) {
+      const int f = it * 32 + lane;
+      const int j = f / (2 * S::RC);
+      const int rem = f - j * (2 * S::RC);
+      const int side = rem / S::RC;
+      const int c = rem - side * S::RC;
+      int64_t p = w0 + j;
+      p = p < a.num_pairs ? p : a.num_pairs - 1;
+      cp_async16(in + (j * S::IN_STRIDE + rem) * 16, (side ? a.z2 : a.z1) + p * S::PER + 2 * c);
+    }
+  }
+}
+
+// one symmetric n x n block from shared memory -> packed lower triangle, symmetrised
+template <int N>
+__device__ __forceinline__ void load_packed_smem(const double* p, double* s) {
+  double buf[N * N];
+  if ((N * N) % 2 == 0) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < N * N / 2; ++i) {
+      const double2 t = p2[i];
+      buf[2 * i] = t.x;
+      buf[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) buf[i] = p[i];
+  }
+  reg::pack_sym<N>(buf, s);
+}
+
+// the warp's 32 staged points (slot stride OUT_STRIDE chunks) -> 32 consecutive points in HBM
+template <int N, int KIND>
+__device__ __forceinline__ void flush_points(const unsigned char* out, double* __restrict__ dst, int64_t w0,
+                                             int64_t num_pairs, int lane) {
+  using S = StageCfg<N, KIND>;
+  double2* d2 = reinterpret_cast<double2*>(dst + w0 * S::PER);
+#pragma unroll
+  for (int it = 0; it < S::RC; ++it) {
+    const int f = it * 32 + lane;
+    const int j = f / S::RC;
+    const int c = f - j * S::RC;
+    if (w0 + j < num_pairs) d2[f] = *reinterpret_cast<const double2*>(out + (j * S::OUT_STRIDE + c) * 16);
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -173,7 +309,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int N, int KIND, int MODE>
-__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_REG_MIN_BLOCKS : 1) pair_kernel(const PairArgs a) {
+__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? (N == 3 ? SY_REG_MIN_BLOCKS_3 : SY_REG_MIN_BLOCKS) : 1)
+    pair_kernel(const PairArgs a) {
   constexpr bool REG = N <= SY_REG_MAX_N;
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;
@@ -187,7 +324,32 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
     for (int k = 0; k < N; ++k) gw_acc[k] = 0.0;
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.num_pairs; base += stride) {
+  using S = StageCfg<N, KIND>;
+  constexpr bool STAGE = S::kOn;
+  const int lane = threadIdx.x & 31;
+  const int wofs = (int)(threadIdx.x & ~31u);  // first pair of this warp within the CTA's batch
+  unsigned char* st_in = nullptr;              // [32 pair slots]   rows of the current / next pairs
+  unsigned char* st_out = nullptr;             // [32 point slots]  unit gradients on their way out
+  longlong2* st_idx = nullptr;                 // [2][32]           index pairs, two generations
+  unsigned bad_next = 0u;                      // lanes whose staged (next) index pair was rejected
+  if (STAGE) {
+    extern __shared__ __align__(16) unsigned char sy_stage_smem[];
+    unsigned char* wb = sy_stage_smem + (threadIdx.x >> 5) * S::warp_bytes(MODE);
+    st_in = wb;
+    st_idx = reinterpret_cast<longlong2*>(wb + S::IN_BYTES);
+    st_out = wb + S::IN_BYTES + S::IDX_BYTES;
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    if (b0 < a.num_pairs) {
+      stage_indices(a, b0 + wofs, st_idx, lane);
+      if (b0 + stride < a.num_pairs) stage_indices(a, b0 + stride + wofs, st_idx + 32, lane);
+      cp_async_wait_all();
+      __syncwarp();
+      bad_next = validate_indices(a, st_idx, lane);
+      stage_rows<N, KIND>(a, b0 + wofs, st_idx, st_in, lane);
+    }
+  }
+  int gen = 0;  // generation (parity) of the index buffer holding the current pairs
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.num_pairs; base += stride, gen ^= 1) {
     if (SY_BLOCK_SYNC && REG && N >= 4) __syncthreads();
     int64_t p = base + threadIdx.x;
     bool active = p < a.num_pairs;
@@ -195,7 +357,26 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
     const double* p1;
     const double* p2;
     int64_t i1 = 0, i2 = 0;
-    if (a.idx != nullptr) {
+    if (STAGE) {
+      cp_async_wait_all();   // rows of this iteration (issued one iteration ago), indices of the next
+      __syncwarp();
+      if (a.idx != nullptr) {
+        if (MODE == kModeStep) {  // only the fused step scatters by row
+          const longlong2 ij = st_idx[gen * 32 + lane];
+          i1 = ij.x;
+          i2 = ij.y;
+        }
+        if ((bad_next >> lane) & 1u) {
+          if (active) {
+            st |= kStatusBadIndex;
+            if (a.dist_out) a.dist_out[p] = 0.0;
+          }
+          active = false;
+        }
+      }
+      p1 = reinterpret_cast<const double*>(st_in + lane * (S::IN_STRIDE * 16));
+      p2 = p1 + S::PER;
+    } else if (a.idx != nullptr) {
       const longlong2 ij = __ldg(reinterpret_cast<const longlong2*>(a.idx) + p);
       i1 = ij.x;
       i2 = ij.y;
@@ -214,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
       p1 = a.z1 + p * PER;
       p2 = a.z2 + p * PER;
     }
-    {  // L2 prefetch of the rows of this thread's next pair
+    if (!STAGE) {  // L2 prefetch of the rows of this thread's next pair
       const int64_t pn = base + stride + threadIdx.x;
       if (pn < a.num_pairs) {
         const double* q1;
@@ -244,15 +425,40 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
     double g1r[GRAD ? T : 1], g1i[GRAD ? T : 1], g2r[GRAD ? T : 1], g2i[GRAD ? T : 1];
     if (KIND == kSpd) {
       double x[T], y[T];
-      load_packed<N, REG>(p1, x);
-      load_packed<N, REG>(p2, y);
+      if (STAGE) {
+        load_packed_smem<N>(p1, x);
+        load_packed_smem<N>(p2, y);
+        __syncwarp();
+        if (base + 2 * stride < a.num_pairs) stage_indices(a, base + 2 * stride + wofs, st_idx + gen * 32, lane);
+        if (base + stride < a.num_pairs) {
+          bad_next = validate_indices(a, st_idx + (gen ^ 1) * 32, lane);
+          stage_rows<N, KIND>(a, base + stride + wofs, st_idx + (gen ^ 1) * 32, st_in, lane);
+        }
+      } else {
+        load_packed<N, REG>(p1, x);
+        load_packed<N, REG>(p2, y);
+      }
       dist = M::template spd<N, GRAD>(x, y, vs, g1r, g2r, &stp);
     } else {
       double x1[T], y1[T], x2[T], y2[T];
-      load_packed<N, REG>(p1, x1);
-      load_packed<N, REG>(p1 + N * N, y1);
-      load_packed<N, REG>(p2, x2);
-      load_packed<N, REG>(p2 + N * N, y2);
+      if (STAGE) {
+        load_packed_smem<N>(p1, x1);
+        load_packed_smem<N>(p1 + N * N, y1);
+        load_packed_smem<N>(p2, x2);
+        load_packed_smem<N>(p2 + N * N, y2);
+        // every lane has its operands in registers: refill the slots with the next pairs' rows
+        __syncwarp();
+        if (base + 2 * stride < a.num_pairs) stage_indices(a, base + 2 * stride + wofs, st_idx + gen * 32, lane);
+        if (base + stride < a.num_pairs) {
+          bad_next = validate_indices(a, st_idx + (gen ^ 1) * 32, lane);
+          stage_rows<N, KIND>(a, base + stride + wofs, st_idx + (gen ^ 1) * 32, st_in, lane);
+        }
+      } else {
+        load_packed<N, REG>(p1, x1);
+        load_packed<N, REG>(p1 + N * N, y1);
+        load_packed<N, REG>(p2, x2);
+        load_packed<N, REG>(p2 + N * N, y2);
+      }
       if (KIND == kUpper)
         dist = M::template upper<N, GRAD>(x1, y1, x2, y2, a.metric, a.wsum_w, vs, g1r, g1i, g2r, g2i, &stp);
       else
@@ -264,7 +470,31 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
 #pragma unroll
       for (int k = 0; k < N; ++k) a.vvd_out[p * N + k] = vs[k];
     }
-    if (active && MODE == kModeFwdSave) {
+    if (STAGE && MODE == kModeFwdSave) {
+      // unit gradients -> own slot -> contiguous segments of the saved state (zeros for a pair whose
+      // indices were rejected; the tail is cut off in flush_points)
+      double* os = reinterpret_cast<double*>(st_out + lane * (S::OUT_STRIDE * 16));
+      if (!active) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+          g1r[i] = 0.0;
+          g2r[i] = 0.0;
+          if (KIND != kSpd) {
+            g1i[i] = 0.0;
+            g2i[i] = 0.0;
+          }
+        }
+      }
+      store_full<N, REG>(os, g1r);
+      if (KIND != kSpd) store_full<N, REG>(os + N * N, g1i);
+      __syncwarp();
+      flush_points<N, KIND>(st_out, a.gz1, base + wofs, a.num_pairs, lane);
+      __syncwarp();
+      store_full<N, REG>(os, g2r);
+      if (KIND != kSpd) store_full<N, REG>(os + N * N, g2i);
+      __syncwarp();
+      flush_points<N, KIND>(st_out, a.gz2, base + wofs, a.num_pairs, lane);
+    } else if (active && MODE == kModeFwdSave) {
       double* o1 = a.gz1 + p * PER;
       double* o2 = a.gz2 + p * PER;
       store_full<N, REG>(o1, g1r);
@@ -298,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? SY_R
       }
     }
   }
+  if (STAGE) cp_async_wait_all();
   if (MODE == kModeStep) {
     loss_acc = warp_sum(loss_acc);
     gscale_acc = warp_sum(gscale_acc);
@@ -320,7 +551,19 @@ template <int N, int KIND, int MODE>
 static int launch_one(const PairArgs& a, cudaStream_t s) {
   // grid-stride launch sized in whole waves of the SM count
   const int grid = grid_for(a.num_pairs, kThreads, 16);
-  pair_kernel<N, KIND, MODE><<<grid, kThreads, 0, s>>>(a);
+  int smem = 0;
+  if (StageCfg<N, KIND>::kOn) {
+    smem = (kThreads / 32) * StageCfg<N, KIND>::warp_bytes(MODE);
+    static bool configured[64] = {};  // per instantiation and device (the attribute is per function per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      if (cudaFuncSetAttribute(pair_kernel<N, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return check_launch();
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+  }
+  pair_kernel<N, KIND, MODE><<<grid, kThreads, smem, s>>>(a);
   return check_launch();
 }
 
