@@ -191,22 +191,33 @@ def run_ours(args):
     # host-resident inputs for the e2e leg
     idx_h = idx.cpu().pin_memory()
     gd_h = gd.cpu().pin_memory()
-    idx_d = torch.empty_like(idx)
-    gd_d = torch.empty_like(gd)
     loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
 
-    def step_e2e():
-        idx_d.copy_(idx_h, non_blocking=True)
-        gd_d.copy_(gd_h, non_blocking=True)
+    from sympa_b200.feeder import PairFeeder
+    feeder = PairFeeder(dev)
+
+    def step_e2e(more):
+        """One step through the public API with HOST inputs: this step's batch was submitted (pinned ->
+        device, side stream) before the previous step's compute was enqueued, the next one is submitted
+        here, the loss is read back and the host waits for it."""
+        idx_b, gd_b = feeder.next()
+        if more:
+            feeder.submit(idx_h, gd_h)
         table.grad = None
-        d = man.dist_from_table(table, idx_d)
-        loss = distortion_loss(gd_d, d * scale)
+        d = man.dist_from_table(table, idx_b)
+        loss = distortion_loss(gd_b, d * scale)
         loss.backward()
+        feeder.done()
         if world > 1:
             sd.allreduce_gradients([table.grad], average=True)
         loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_h[0])
+
+    def run_e2e(steps):
+        feeder.submit(idx_h, gd_h)            # first batch: its copy is exposed, and inside the timed region
+        for s in range(steps):
+            step_e2e(s + 1 < steps)
 
     def barrier():
         if world > 1:
@@ -281,14 +292,12 @@ def run_ours(args):
     del gt
 
     # e2e
-    for _ in range(3):
-        step_e2e()
+    run_e2e(3)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -332,7 +341,11 @@ def run_ours(args):
                    "l2": "table + saved unit gradients + indices exceed L2 every step (no explicit flush needed)",
                    "parallelism": f"dp{world} pairs sharded, table replicated, one NCCL all-reduce of the table gradient"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(idx_h.numel() * 8 + gd_h.numel() * 8),
-                "d2h_bytes_per_step": 8},
+                "d2h_bytes_per_step": 8,
+                "how": "manifold.dist_from_table + AverageDistortionLoss + backward per step; every step's index pairs and "
+                       "graph distances are copied from pinned host memory (sympa_b200.feeder.PairFeeder: the copy of step "
+                       "k+1 overlaps the compute of step k on a side stream; the first copy is exposed), the loss is read "
+                       "back and the host waits for it every step"},
         "gpu_launches": 2 * args.steps,
         "fused_step": {"pairs_per_s": world * b / (ms_fused * 1e-3), "ms_per_step": ms_fused, "launches_per_step": 1},
         "clocks": clocks,

@@ -41,9 +41,11 @@ struct WarpExec {
 #pragma unroll 1
     for (; sweep < kMaxSweeps; ++sweep) {
       unsigned conv = 0u;
+      double tn = coop::column_norm2<N, IS_REAL>(tr, ti);  // squared norms, carried through the sweep
+      double bn = coop::column_norm2<N, IS_REAL>(br, bi);
 #pragma unroll 1
       for (int r = 0; r < NP - 1; ++r) {
-        if (!done) conv |= coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi);
+        if (!done) conv |= coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi, &tn, &bn);
         if (G > 1) {
           const bool first = g == 0, last = g == G - 1;
 #pragma unroll
@@ -60,6 +62,13 @@ struct WarpExec {
               ti[i] = first ? old_ti : up_i;
               bi[i] = last ? old_ti : dn_i;
             }
+          }
+          {
+            const double up_n = __shfl_up_sync(kFull, first ? bn : tn, 1);
+            const double dn_n = __shfl_down_sync(kFull, bn, 1);
+            const double old_tn = tn;
+            tn = first ? old_tn : up_n;
+            bn = last ? old_tn : dn_n;
           }
           const int up_id = __shfl_up_sync(kFull, first ? bid : tid, 1);
           const int dn_id = __shfl_down_sync(kFull, bid, 1);

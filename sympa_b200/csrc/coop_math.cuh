@@ -298,17 +298,26 @@ SY_HD void tournament(int r, int k, int* p, int* q) {
 // Orthogonalise one column pair held in registers (complex, or real when IS_REAL).  Returns the
 // convergence flags of the pair (kConvLoose | kConvStrict | kConvClose, see jacobi_rotation).
 template <int N, bool IS_REAL>
-SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi) {
-  // two partial sums per quantity: shorter dependency chains
-  double al0 = 0.0, be0 = 0.0, cr0 = 0.0, ci0 = 0.0, al1 = 0.0, be1 = 0.0, cr1 = 0.0, ci1 = 0.0;
+SY_HD double column_norm2(const double* pr, const double* pi) {
+  double a0 = 0.0, a1 = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    al0 += pr[i] * pr[i];
-    be0 += qr[i] * qr[i];
+    a0 += pr[i] * pr[i];
+    if (!IS_REAL) a1 += pi[i] * pi[i];
+  }
+  return a0 + a1;
+}
+
+// *pn, *qn: the squared norms of the two columns, carried along with them (recomputed by the caller
+// at the start of every sweep, updated here: see reg::jacobi_svd).
+template <int N, bool IS_REAL>
+SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi, double* pn, double* qn) {
+  // two partial sums per quantity: shorter dependency chains
+  double cr0 = 0.0, ci0 = 0.0, cr1 = 0.0, ci1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
     cr0 += pr[i] * qr[i];
     if (!IS_REAL) {
-      al1 += pi[i] * pi[i];
-      be1 += qi[i] * qi[i];
       cr1 += pi[i] * qi[i];
       ci0 += pr[i] * qi[i];
       ci1 += pi[i] * qr[i];
@@ -316,7 +325,7 @@ SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi) {
   }
   unsigned conv = 0u;
   double c, sr, si, xf;
-  if (loc::jacobi_rotation(al0 + al1, be0 + be1, cr0 + cr1, ci0 - ci1, loc::jacobi_stop_ratio2<N>(), &c, &sr, &si, &xf, &conv)) {
+  if (loc::jacobi_rotation(*pn, *qn, cr0 + cr1, ci0 - ci1, loc::jacobi_stop_ratio2<N>(), &c, &sr, &si, &xf, &conv)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double a0 = pr[i], b0 = qr[i];
@@ -331,6 +340,8 @@ SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi) {
         qi[i] = c * b1 + (sr * a1 + si * a0);
       }
     }
+    *pn -= xf;
+    *qn += xf;
   }
   return conv;
 }
@@ -361,22 +372,29 @@ inline int jacobi_ring_host(int G, double* gr, double* gi) {
     }
   }
   int sweep = 0;
+  double tn[L::G], bn[L::G];  // carried squared column norms
   for (; sweep < kMaxSweeps; ++sweep) {
     unsigned conv = 0u;
+    for (int g = 0; g < G; ++g) {
+      tn[g] = column_norm2<N, IS_REAL>(tr[g], ti[g]);
+      bn[g] = column_norm2<N, IS_REAL>(br[g], bi[g]);
+    }
     for (int r = 0; r < NP - 1; ++r) {
-      for (int g = 0; g < G; ++g) conv |= rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g]);
+      for (int g = 0; g < G; ++g) conv |= rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g], &tn[g], &bn[g]);
       if (G > 1) {
-        double ntr[L::G][N], nti[L::G][N], nbr[L::G][N], nbi[L::G][N];
+        double ntr[L::G][N], nti[L::G][N], nbr[L::G][N], nbi[L::G][N], ntn[L::G], nbn[L::G];
         int ntid[L::G], nbid[L::G];
         for (int g = 0; g < G; ++g) {
           // new top: lane 0 keeps its top, lane 1 takes lane 0's bottom, lane g takes lane g-1's top
           const double* sr_ = g == 0 ? tr[0] : (g == 1 ? br[0] : tr[g - 1]);
           const double* si_ = g == 0 ? ti[0] : (g == 1 ? bi[0] : ti[g - 1]);
           ntid[g] = g == 0 ? tid[0] : (g == 1 ? bid[0] : tid[g - 1]);
+          ntn[g] = g == 0 ? tn[0] : (g == 1 ? bn[0] : tn[g - 1]);
           // new bottom: lane g takes lane g+1's bottom, the last lane takes its own top
           const double* ur_ = g == G - 1 ? tr[g] : br[g + 1];
           const double* ui_ = g == G - 1 ? ti[g] : bi[g + 1];
           nbid[g] = g == G - 1 ? tid[g] : bid[g + 1];
+          nbn[g] = g == G - 1 ? tn[g] : bn[g + 1];
           for (int i = 0; i < N; ++i) {
             ntr[g][i] = sr_[i];
             nti[g][i] = si_[i];
@@ -387,6 +405,8 @@ inline int jacobi_ring_host(int G, double* gr, double* gi) {
         for (int g = 0; g < G; ++g) {
           tid[g] = ntid[g];
           bid[g] = nbid[g];
+          tn[g] = ntn[g];
+          bn[g] = nbn[g];
           for (int i = 0; i < N; ++i) {
             tr[g][i] = ntr[g][i];
             ti[g][i] = nti[g][i];

@@ -91,6 +91,11 @@ constexpr int kThreads = SY_PAIR_THREADS;
 #ifndef SY_REG_MIN_BLOCKS_3
 #define SY_REG_MIN_BLOCKS_3 SY_REG_MIN_BLOCKS
 #endif
+// the forward-only kernel (evaluation, distance matrices) keeps less state alive: 3 CTAs/SM at 168
+// registers measured +10 % (n = 4) and +7 % (n = 3) over 2 CTAs/SM (n = 5, 6 would spill: left at 2)
+#ifndef SY_FWD_MIN_BLOCKS
+#define SY_FWD_MIN_BLOCKS 3
+#endif
 
 // namespace switch: reg = unrolled / registers (N <= SY_REG_MAX_N), loc = rolled / local memory
 template <bool REG>
@@ -199,12 +204,14 @@ struct StageCfg {
                               (KIND != kSpd);
   static constexpr int RC = PER / 2;                           // 16-byte chunks per point
   static constexpr int IN_STRIDE = 2 * RC + 1;                 // chunks per pair slot (two points + pad)
-  static constexpr int OUT_STRIDE = (RC % 2 == 0) ? RC + 1 : RC;
+  // point slot on the way out: RC chunks + one pad chunk (carries the destination row in the fused
+  // step), rounded up to an odd number of chunks
+  static constexpr int OUT_STRIDE = (RC % 2 == 0) ? RC + 1 : RC + 2;
   static constexpr int IN_BYTES = 32 * IN_STRIDE * 16;
   static constexpr int OUT_BYTES = 32 * OUT_STRIDE * 16;
   static constexpr int IDX_BYTES = 2 * 32 * 16;                // two generations of 32 index pairs
-  // per-warp layout: [rows in][indices][unit gradients out - only the forward+save kernel has them]
-  __host__ __device__ static constexpr int warp_bytes(int mode) { return IN_BYTES + IDX_BYTES + (mode == 1 ? OUT_BYTES : 0); }
+  // per-warp layout: [rows in][indices][gradients out - not in the forward-only kernel]
+  __host__ __device__ static constexpr int warp_bytes(int mode) { return IN_BYTES + IDX_BYTES + (mode != 0 ? OUT_BYTES : 0); }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -298,7 +305,23 @@ __device__ __forceinline__ void flush_points(const unsigned char* out, double* _
     const int f = it * 32 + lane;
     const int j = f / S::RC;
     const int c = f - j * S::RC;
-    if (w0 + j < num_pairs) d2[f] = *reinterpret_cast<const double2*>(out + (j * S::OUT_STRIDE + c) * 16);
+    if (w0 + j < num_pairs) __stcs(d2 + f, *reinterpret_cast<const double2*>(out + (j * S::OUT_STRIDE + c) * 16));
+  }
+}
+
+// the warp's 32 staged (already scaled) point gradients -> scatter-add into the table gradient,
+// consecutive lanes on consecutive elements of a row (one 32-byte sector per four lanes instead of
+// one per lane).  The pad chunk of a slot holds the destination row, or -1 for "no contribution".
+template <int N, int KIND>
+__device__ __forceinline__ void flush_atomic(const unsigned char* out, double* __restrict__ grad_table, int lane) {
+  using S = StageCfg<N, KIND>;
+#pragma unroll
+  for (int it = 0; it < S::PER; ++it) {
+    const int f = it * 32 + lane;
+    const int j = f / S::PER;
+    const int e = f - j * S::PER;
+    const int64_t r = *reinterpret_cast<const int64_t*>(out + (j * S::OUT_STRIDE + S::RC) * 16);
+    if (r >= 0) atomicAdd(grad_table + r * S::PER + e, *reinterpret_cast<const double*>(out + j * S::OUT_STRIDE * 16 + e * 8));
   }
 }
 
@@ -309,7 +332,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int N, int KIND, int MODE>
-__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? (N == 3 ? SY_REG_MIN_BLOCKS_3 : SY_REG_MIN_BLOCKS) : 1)
+__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3)
+                                                ? ((MODE == 0 && N <= 4) ? SY_FWD_MIN_BLOCKS : (N == 3 ? SY_REG_MIN_BLOCKS_3 : SY_REG_MIN_BLOCKS))
+                                                : 1)
     pair_kernel(const PairArgs a) {
   constexpr bool REG = N <= SY_REG_MAX_N;
   constexpr int T = Cfg<N>::kTri;
@@ -518,14 +543,42 @@ __global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3) ? (N =
 #pragma unroll
         for (int k = 0; k < N; ++k) gw_acc[k] += (a.wsum_w[k] > 0.0) ? dl_dd * vs[k] : 0.0;
       }
-      double* o1 = a.grad_table + i1 * PER;
-      double* o2 = a.grad_table + i2 * PER;
-      atomic_add_full<N, REG>(o1, g1r, dl_dd);
-      atomic_add_full<N, REG>(o2, g2r, dl_dd);
-      if (KIND != kSpd) {
-        atomic_add_full<N, REG>(o1 + N * N, g1i, dl_dd);
-        atomic_add_full<N, REG>(o2 + N * N, g2i, dl_dd);
+      if (STAGE) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+          g1r[i] *= dl_dd;
+          g2r[i] *= dl_dd;
+          if (KIND != kSpd) {
+            g1i[i] *= dl_dd;
+            g2i[i] *= dl_dd;
+          }
+        }
+      } else {
+        double* o1 = a.grad_table + i1 * PER;
+        double* o2 = a.grad_table + i2 * PER;
+        atomic_add_full<N, REG>(o1, g1r, dl_dd);
+        atomic_add_full<N, REG>(o2, g2r, dl_dd);
+        if (KIND != kSpd) {
+          atomic_add_full<N, REG>(o1 + N * N, g1i, dl_dd);
+          atomic_add_full<N, REG>(o2 + N * N, g2i, dl_dd);
+        }
       }
+    }
+    if (STAGE && MODE == kModeStep) {
+      // scaled gradients -> own slot (+ destination row in the pad chunk) -> row-contiguous atomics
+      double* os = reinterpret_cast<double*>(st_out + lane * (S::OUT_STRIDE * 16));
+      int64_t* orow = reinterpret_cast<int64_t*>(st_out + (lane * S::OUT_STRIDE + S::RC) * 16);
+      store_full<N, REG>(os, g1r);
+      if (KIND != kSpd) store_full<N, REG>(os + N * N, g1i);
+      *orow = active ? i1 : -1;
+      __syncwarp();
+      flush_atomic<N, KIND>(st_out, a.grad_table, lane);
+      __syncwarp();
+      store_full<N, REG>(os, g2r);
+      if (KIND != kSpd) store_full<N, REG>(os + N * N, g2i);
+      *orow = active ? i2 : -1;
+      __syncwarp();
+      flush_atomic<N, KIND>(st_out, a.grad_table, lane);
     }
   }
   if (STAGE) cp_async_wait_all();

