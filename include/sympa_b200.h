@@ -104,6 +104,17 @@ int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs,
                        double* scratch, int64_t scratch_bytes,
                        unsigned int* status, void* stream);
 
+/* All-pairs evaluation: rows [row_begin, row_begin + row_count) of the
+ * (num_rows x num_rows) matrix of manifold distances between the points of `table`, written row-major
+ * into dist_out (row_count x num_rows) with exact zeros on the diagonal.  Replaces
+ * Runner.build_distance_matrix (sympa/runner.py:142-154: num_rows forward calls of batch num_rows,
+ * the diagonal entry asked for a neighbour and then overwritten with 0) by forward launches over
+ * chunks of workspace_pairs pairs whose index pairs are generated on the device into idx_workspace
+ * (2 * workspace_pairs int64, caller-allocated, contents irrelevant).  Forward only. */
+int sympa_dist_matrix(int kind, int n, int metric, const double* table, int64_t num_rows,
+                      int64_t row_begin, int64_t row_count, const double* wsum_w, double* dist_out,
+                      int64_t* idx_workspace, int64_t workspace_pairs, unsigned int* status, void* stream);
+
 /* Backward: replaces autograd through the ~250 torch ops of dist plus the gather backward.
  * grad_dist (num_pairs) is dL/d dist.  Materialised form: grad_z1 / grad_z2 are OVERWRITTEN with
  * the (symmetric) gradients.  Table form: grad_table (num_rows, point) is ACCUMULATED into with

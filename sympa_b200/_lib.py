@@ -31,6 +31,7 @@ EXPORTS = (
     "sympa_dist_forward",
     "sympa_dist_backward",
     "sympa_distortion_step",
+    "sympa_dist_matrix",
 )
 
 _lib = None
@@ -70,6 +71,8 @@ def load():
     lib.sympa_dist_backward.argtypes = [I, I, I, L, P, P, P, P, P, L, P, P, P, P, P]
     lib.sympa_distortion_step.restype = I
     lib.sympa_distortion_step.argtypes = [I, I, I, L, P, L, P, P, D, P, P, P, P, P, P, P, L, P, P]
+    lib.sympa_dist_matrix.restype = I
+    lib.sympa_dist_matrix.argtypes = [I, I, I, P, L, L, L, P, P, P, L, P, P]
     _lib = lib
     return lib
 

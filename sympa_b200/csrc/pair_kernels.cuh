@@ -200,7 +200,7 @@ template <int N, int KIND>
 struct StageCfg {
   static constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;  // doubles per point
   // (spd at n = 4 runs 3 CTAs/SM at 160 registers and measured slower with the staging: left per-thread)
-  static constexpr bool kOn = (N >= SY_STAGE_MIN_N) && (N <= SY_STAGE_MAX_N) && (N <= SY_REG_MAX_N) && (PER % 2 == 0) &&
+  static constexpr bool kOn = (N >= SY_STAGE_MIN_N) && (N <= SY_STAGE_MAX_N) && (N <= reg_max_n(KIND)) && (PER % 2 == 0) &&
                               (KIND != kSpd);
   static constexpr int RC = PER / 2;                           // 16-byte chunks per point
   static constexpr int IN_STRIDE = 2 * RC + 1;                 // chunks per pair slot (two points + pad)
@@ -332,11 +332,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int N, int KIND, int MODE>
-__global__ void __launch_bounds__(kThreads, (N <= SY_REG_MAX_N && N >= 3)
+__global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
                                                 ? ((MODE == 0 && N <= 4) ? SY_FWD_MIN_BLOCKS : (N == 3 ? SY_REG_MIN_BLOCKS_3 : SY_REG_MIN_BLOCKS))
                                                 : 1)
     pair_kernel(const PairArgs a) {
-  constexpr bool REG = N <= SY_REG_MAX_N;
+  constexpr bool REG = N <= reg_max_n(KIND);
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;
   constexpr bool GRAD = MODE != kModeFwd;
@@ -625,14 +625,14 @@ static int launch_coop(const PairArgs& a, cudaStream_t s);  // coop_kernels.cuh
 template <int N, int MODE>
 static int launch_split(const PairArgs& a, double* scratch, int64_t cap, cudaStream_t s);
 
-// kernel selection: one pair per thread in registers for n <= SY_REG_MAX_N; warp-cooperative shared
+// kernel selection: one pair per thread in registers for n <= reg_max_n(kind); warp-cooperative shared
 // memory kernel for the larger upper-half sizes; rolled per-thread fallback otherwise.
 template <int N, int KIND, int MODE>
 static int launch_any(const PairArgs& a, cudaStream_t s) {
-  if constexpr (KIND == kUpper && (N > SY_REG_MAX_N)) {
+  if constexpr (KIND == kUpper && (N > reg_max_n(kUpper))) {
     if (a.scratch != nullptr && a.scratch_pairs > 0) return launch_split<N, MODE>(a, a.scratch, a.scratch_pairs, s);
     return launch_coop<N, KIND, MODE>(a, s);
-  } else if constexpr (N > SY_REG_MAX_N) {   // spd, bounded
+  } else if constexpr (N > reg_max_n(KIND)) {   // spd, bounded
     return launch_coop<N, KIND, MODE>(a, s);
   } else {
     return launch_one<N, KIND, MODE>(a, s);

@@ -85,6 +85,28 @@ __global__ void __launch_bounds__(256) wsum_grad_kernel(int64_t num_pairs, int n
   }
 }
 
+// index pairs of a block of the all-pairs distance matrix: pair t of the chunk is entry first + t of the
+// row-major (row_count x num_rows) block whose first row is row_begin.  The diagonal asks for the
+// next node instead (its entry is overwritten with 0 afterwards), as sympa/runner.py:148 does.
+__global__ void __launch_bounds__(256) all_pairs_index_kernel(int64_t first, int64_t count, int64_t num_rows,
+                                                              int64_t row_begin, longlong2* __restrict__ idx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    const int64_t e = first + t;
+    const int64_t r = e / num_rows;
+    const int64_t j = e - r * num_rows;
+    int64_t i = row_begin + r;
+    if (i == j) i = (i + 1) % num_rows;
+    idx[t] = make_longlong2(i, j);
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_diagonal_kernel(int64_t row_begin, int64_t row_count, int64_t num_rows,
+                                                            double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < row_count && row_begin + r < num_rows) out[r * num_rows + row_begin + r] = 0.0;
+}
+
 // FP64 FMA throughput probe (diagnostic: gives bench.py a MEASURED FP64 roofline denominator; the
 // driver's MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).  8 independent FMA chains/thread.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed, double* __restrict__ out) {
@@ -297,6 +319,32 @@ int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs, const dou
   }
   setup_scratch(&a, kind, n, scratch, scratch_bytes, false);
   return launch_n(n, kind, saved_state != nullptr ? kModeFwdSave : kModeFwd, a, (cudaStream_t)stream);
+}
+
+int sympa_dist_matrix(int kind, int n, int metric, const double* table, int64_t num_rows, int64_t row_begin,
+                      int64_t row_count, const double* wsum_w, double* dist_out, int64_t* idx_workspace,
+                      int64_t workspace_pairs, unsigned int* status, void* stream) {
+  if (!valid_common(kind, n, metric, 0)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (table == nullptr || dist_out == nullptr || idx_workspace == nullptr || workspace_pairs <= 0) return SYMPA_ERR_BAD_ARG;
+  if (num_rows <= 0 || row_begin < 0 || row_count < 0 || row_begin + row_count > num_rows) return SYMPA_ERR_BAD_ARG;
+  if (metric == SYMPA_METRIC_WSUM && kind != SYMPA_KIND_SPD && wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t total = row_count * num_rows;
+  for (int64_t first = 0; first < total; first += workspace_pairs) {
+    const int64_t count = (total - first) < workspace_pairs ? (total - first) : workspace_pairs;
+    all_pairs_index_kernel<<<grid_for(count, 256, 8), 256, 0, s>>>(first, count, num_rows, row_begin,
+                                                                 reinterpret_cast<longlong2*>(idx_workspace));
+    int rc = check_launch();
+    if (rc) return rc;
+    rc = sympa_dist_forward(kind, n, metric, count, nullptr, nullptr, table, num_rows, idx_workspace, wsum_w,
+                            dist_out + first, nullptr, nullptr, nullptr, 0, status, stream);
+    if (rc) return rc;
+  }
+  if (row_count > 0) {
+    zero_diagonal_kernel<<<(int)((row_count + 255) / 256), 256, 0, s>>>(row_begin, row_count, num_rows, dist_out);
+    return check_launch();
+  }
+  return SYMPA_OK;
 }
 
 int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const double* grad_dist,

@@ -60,6 +60,12 @@ class SiegelManifold(Manifold, ABC):
         d, _ = ops.table_dist(self.kind, self.metric.name, table, idx, self._wsum(table))
         return d
 
+    def dist_matrix(self, table: torch.Tensor, row_begin: int = 0, row_count=None) -> torch.Tensor:
+        """All-pairs distances between the rows of `table` (rows [row_begin, row_begin + row_count) of the
+        matrix, zeros on the diagonal, forward only): what Runner.build_distance_matrix
+        (sympa/runner.py:142-154) assembles with one dist call per node."""
+        return ops.dist_matrix(self.kind, self.metric.name, table, row_begin, row_count, self._wsum(table))
+
     # ------------------------------------------------------------------ optimizer side
     def retr(self, x: torch.Tensor, u: torch.Tensor) -> torch.Tensor:  # siegel_manifold.py:74-87
         return self.projx(x + u)

@@ -38,6 +38,10 @@ class SymmetricPositiveDefinite(Manifold):
         d, _ = ops.table_dist("spd", "riem", table, idx)
         return d
 
+    def dist_matrix(self, table, row_begin=0, row_count=None):
+        """all-pairs distances between the rows of `table` (see SiegelManifold.dist_matrix)"""
+        return ops.dist_matrix("spd", "riem", table, row_begin, row_count)
+
     def egrad2rgrad(self, x, u):
         return x @ sm.sym(u) @ x.transpose(-1, -2)
 

@@ -26,6 +26,21 @@ class Model(nn.Module):
     def distance(self, src_embeds, dst_embeds):   # model.py:32-38
         return self.manifold.dist(src_embeds, dst_embeds)
 
+    def build_distance_matrix(self, rows_per_call=None):
+        """(N, N) matrix of scaled manifold distances between all embeddings, zeros on the diagonal
+        (Runner.build_distance_matrix, sympa/runner.py:142-154, which calls the model once per node):
+        forward-only launches over chunks of pairs, indices generated on the device."""
+        table = self.embeddings.embeds.detach()
+        n_pts = table.shape[0]
+        with torch.no_grad():
+            if rows_per_call is None:
+                return self.manifold.dist_matrix(table) * self.get_scale()
+            out = torch.empty(n_pts, n_pts, dtype=torch.float64, device=table.device)
+            for r0 in range(0, n_pts, rows_per_call):
+                rc = min(rows_per_call, n_pts - r0)
+                out[r0:r0 + rc] = self.manifold.dist_matrix(table, r0, rc) * self.get_scale()
+            return out
+
     def get_scale(self):   # model.py:40-41
         return (self.scale / self.scale_coef).clamp_min(0.1)
 

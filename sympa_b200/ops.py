@@ -239,6 +239,41 @@ def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsu
     return loss_out
 
 
+_idx_workspace = {}
+
+
+def dist_matrix(kind, metric, table, row_begin=0, row_count=None, wsum_w=None, chunk_pairs=1 << 24):
+    """Rows [row_begin, row_begin + row_count) of the all-pairs distance matrix of `table` (forward only,
+    zeros on the diagonal): sympa_dist_matrix.  The index workspace (16 bytes per pair of a chunk) is
+    kept per device and reused."""
+    lib = _lib.load()
+    table = _require(table, "table").detach()
+    n = table.shape[-1]
+    _check_n(n)
+    rows = table.shape[0]
+    row_count = rows - row_begin if row_count is None else row_count
+    if row_begin < 0 or row_count < 0 or row_begin + row_count > rows:
+        raise ValueError("row range outside the table")
+    if metric == "wsum" and kind != "spd":
+        wsum_w = _require(wsum_w, "wsum_w").reshape(-1)
+    else:
+        wsum_w = None
+    dev = table.device
+    with torch.cuda.device(dev):
+        out = torch.empty(row_count, rows, dtype=torch.float64, device=dev)
+        if row_count == 0 or rows == 0:
+            return out
+        chunk = max(1, min(chunk_pairs, row_count * rows))
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        ws = _idx_workspace.get(key)
+        if ws is None or ws.numel() < 2 * chunk:
+            ws = torch.empty(2 * chunk, dtype=torch.int64, device=dev)
+            _idx_workspace[key] = ws
+        _lib.check(lib.sympa_dist_matrix(_lib.KIND[kind], n, _lib.METRIC[metric], _ptr(table), rows, row_begin, row_count,
+                                         _ptr(wsum_w), _ptr(out), _ptr(ws), chunk, _ptr(status_word(dev)), _stream()))
+    return out
+
+
 def rsgd_step(kind, table, grad, lr, lr_scale=None, projected=None):
     """In-place Riemannian SGD update of a CUDA table (one launch); see sympa_rsgd_step in the header."""
     lib = _lib.load()

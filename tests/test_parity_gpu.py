@@ -410,3 +410,40 @@ def test_far_apart_and_nearly_coincident_pairs(sb, n):
         np.testing.assert_allclose(d.detach().cpu().numpy(), d_ref.numpy(), rtol=1e-4, atol=1e-13)
         assert torch.isfinite(a1.grad).all()
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n,metric", [("upper", 3, "riem"), ("bounded", 4, "fone"), ("upper", 7, "fmin"), ("spd", 4, "riem")])
+def test_distance_matrix_matches_oracle_and_reference_semantics(sb, kind, n, metric):
+    """Model.build_distance_matrix / manifold.dist_matrix against the oracle evaluated
+    the way Runner.build_distance_matrix does (sympa/runner.py:142-154): row by row, exact zeros on the
+    diagonal; the chunking (index workspace smaller than the matrix) and row blocks must not matter."""
+    rows = 37
+    g = torch.Generator().manual_seed(11)
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g)
+        man = sb.SymmetricPositiveDefinite().cuda()
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+        man = make_manifold(sb, kind, n, metric)
+    ref = torch.zeros(rows, rows, dtype=torch.float64)
+    allr = torch.arange(rows)
+    for i in range(rows):
+        src = torch.full((rows,), i)
+        src[i] = (i + 1) % rows
+        d = so.dist(kind, table[src], table[allr], metric)
+        d[i] = 0
+        ref[i] = d
+    t = table.cuda()
+    full = man.dist_matrix(t)
+    assert full.shape == (rows, rows)
+    torch.testing.assert_close(full.cpu(), ref, rtol=RTOL, atol=ATOL)
+    assert torch.all(torch.diagonal(full) == 0)
+    # small index workspace (several chunks per call) and a row block
+    small = sb.ops.dist_matrix(kind, metric if kind != "spd" else "riem", t, chunk_pairs=100)
+    assert torch.equal(small, full)
+    block = man.dist_matrix(t, 5, 9)
+    assert torch.equal(block, full[5:14])
+    assert man.dist_matrix(t, 3, 0).shape == (0, rows)
+    sb.ops.check_status()
