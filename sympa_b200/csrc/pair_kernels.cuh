@@ -163,6 +163,24 @@ __device__ __forceinline__ void store_full(double* __restrict__ out, const doubl
   }
 }
 
+// packed lower triangles of one point's unit gradient (re, then im unless spd) -> saved state
+template <int N, bool HAS_IM>
+__device__ __forceinline__ void store_state(double* __restrict__ out, const double* re, const double* im) {
+  constexpr int T = Cfg<N>::kTri;
+  constexpr int TOT = (HAS_IM ? 2 : 1) * T;
+  if (TOT % 2 == 0) {
+    double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+    for (int e = 0; e < TOT / 2; ++e) {
+      const int a = 2 * e, b = 2 * e + 1;
+      o2[e] = make_double2(a < T ? re[a] : im[a - T], b < T ? re[b] : im[b - T]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < TOT; ++e) out[e] = e < T ? re[e] : im[e - T];
+  }
+}
+
 template <int N, bool REG>
 __device__ __forceinline__ void atomic_add_full(double* __restrict__ out, const double* s, double scale) {
   if (REG) {
@@ -204,14 +222,18 @@ struct StageCfg {
                               (KIND != kSpd);
   static constexpr int RC = PER / 2;                           // 16-byte chunks per point
   static constexpr int IN_STRIDE = 2 * RC + 1;                 // chunks per pair slot (two points + pad)
-  // point slot on the way out: RC chunks + one pad chunk (carries the destination row in the fused
-  // step), rounded up to an odd number of chunks
-  static constexpr int OUT_STRIDE = (RC % 2 == 0) ? RC + 1 : RC + 2;
+  // point slot on the way out: the fused step (mode 2) stages full points (RC chunks) for its atomics,
+  // the forward+save kernel (mode 1) packed saved state (SRC chunks); plus one pad chunk (carries the
+  // destination row in the fused step), rounded up to an odd number of chunks
+  static constexpr int SRC = state_doubles(KIND, N) / 2;
+  __host__ __device__ static constexpr int out_rc(int mode) { return mode == 2 ? RC : SRC; }
+  __host__ __device__ static constexpr int out_stride(int mode) { return (out_rc(mode) % 2 == 0) ? out_rc(mode) + 1 : out_rc(mode) + 2; }
   static constexpr int IN_BYTES = 32 * IN_STRIDE * 16;
-  static constexpr int OUT_BYTES = 32 * OUT_STRIDE * 16;
   static constexpr int IDX_BYTES = 2 * 32 * 16;                // two generations of 32 index pairs
   // per-warp layout: [rows in][indices][gradients out - not in the forward-only kernel]
-  __host__ __device__ static constexpr int warp_bytes(int mode) { return IN_BYTES + IDX_BYTES + (mode != 0 ? OUT_BYTES : 0); }
+  __host__ __device__ static constexpr int warp_bytes(int mode) {
+    return IN_BYTES + IDX_BYTES + (mode != 0 ? 32 * out_stride(mode) * 16 : 0);
+  }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -294,18 +316,19 @@ __device__ __forceinline__ void load_packed_smem(const double* p, double* s) {
   reg::pack_sym<N>(buf, s);
 }
 
-// the warp's 32 staged points (slot stride OUT_STRIDE chunks) -> 32 consecutive points in HBM
+// the warp's 32 staged points of saved state (slot stride out_stride(1) chunks) -> 32 consecutive points in HBM
 template <int N, int KIND>
 __device__ __forceinline__ void flush_points(const unsigned char* out, double* __restrict__ dst, int64_t w0,
                                              int64_t num_pairs, int lane) {
   using S = StageCfg<N, KIND>;
-  double2* d2 = reinterpret_cast<double2*>(dst + w0 * S::PER);
+  constexpr int RC = S::out_rc(1), STRIDE = S::out_stride(1);
+  double2* d2 = reinterpret_cast<double2*>(dst + w0 * (2 * RC));
 #pragma unroll
-  for (int it = 0; it < S::RC; ++it) {
+  for (int it = 0; it < RC; ++it) {
     const int f = it * 32 + lane;
-    const int j = f / S::RC;
-    const int c = f - j * S::RC;
-    if (w0 + j < num_pairs) __stcs(d2 + f, *reinterpret_cast<const double2*>(out + (j * S::OUT_STRIDE + c) * 16));
+    const int j = f / RC;
+    const int c = f - j * RC;
+    if (w0 + j < num_pairs) __stcs(d2 + f, *reinterpret_cast<const double2*>(out + (j * STRIDE + c) * 16));
   }
 }
 
@@ -315,13 +338,14 @@ __device__ __forceinline__ void flush_points(const unsigned char* out, double* _
 template <int N, int KIND>
 __device__ __forceinline__ void flush_atomic(const unsigned char* out, double* __restrict__ grad_table, int lane) {
   using S = StageCfg<N, KIND>;
+  constexpr int STRIDE = S::out_stride(2);
 #pragma unroll
   for (int it = 0; it < S::PER; ++it) {
     const int f = it * 32 + lane;
     const int j = f / S::PER;
     const int e = f - j * S::PER;
-    const int64_t r = *reinterpret_cast<const int64_t*>(out + (j * S::OUT_STRIDE + S::RC) * 16);
-    if (r >= 0) atomicAdd(grad_table + r * S::PER + e, *reinterpret_cast<const double*>(out + j * S::OUT_STRIDE * 16 + e * 8));
+    const int64_t r = *reinterpret_cast<const int64_t*>(out + (j * STRIDE + S::RC) * 16);
+    if (r >= 0) atomicAdd(grad_table + r * S::PER + e, *reinterpret_cast<const double*>(out + j * STRIDE * 16 + e * 8));
   }
 }
 
@@ -498,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
     if (STAGE && MODE == kModeFwdSave) {
       // unit gradients -> own slot -> contiguous segments of the saved state (zeros for a pair whose
       // indices were rejected; the tail is cut off in flush_points)
-      double* os = reinterpret_cast<double*>(st_out + lane * (S::OUT_STRIDE * 16));
+      double* os = reinterpret_cast<double*>(st_out + lane * (S::out_stride(1) * 16));
       if (!active) {
 #pragma unroll
         for (int i = 0; i < T; ++i) {
@@ -510,23 +534,27 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
           }
         }
       }
-      store_full<N, REG>(os, g1r);
-      if (KIND != kSpd) store_full<N, REG>(os + N * N, g1i);
+      store_state<N, KIND != kSpd>(os, g1r, g1i);
       __syncwarp();
       flush_points<N, KIND>(st_out, a.gz1, base + wofs, a.num_pairs, lane);
       __syncwarp();
-      store_full<N, REG>(os, g2r);
-      if (KIND != kSpd) store_full<N, REG>(os + N * N, g2i);
+      store_state<N, KIND != kSpd>(os, g2r, g2i);
       __syncwarp();
       flush_points<N, KIND>(st_out, a.gz2, base + wofs, a.num_pairs, lane);
     } else if (active && MODE == kModeFwdSave) {
-      double* o1 = a.gz1 + p * PER;
-      double* o2 = a.gz2 + p * PER;
-      store_full<N, REG>(o1, g1r);
-      store_full<N, REG>(o2, g2r);
-      if (KIND != kSpd) {
-        store_full<N, REG>(o1 + N * N, g1i);
-        store_full<N, REG>(o2 + N * N, g2i);
+      if (REG) {  // packed saved state (state_is_packed)
+        constexpr int PS = state_doubles(KIND, N);
+        store_state<N, KIND != kSpd>(a.gz1 + p * PS, g1r, g1i);
+        store_state<N, KIND != kSpd>(a.gz2 + p * PS, g2r, g2i);
+      } else {
+        double* o1 = a.gz1 + p * PER;
+        double* o2 = a.gz2 + p * PER;
+        store_full<N, REG>(o1, g1r);
+        store_full<N, REG>(o2, g2r);
+        if (KIND != kSpd) {
+          store_full<N, REG>(o1 + N * N, g1i);
+          store_full<N, REG>(o2 + N * N, g2i);
+        }
       }
     }
     if (active && MODE == kModeStep) {
@@ -566,8 +594,8 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
     }
     if (STAGE && MODE == kModeStep) {
       // scaled gradients -> own slot (+ destination row in the pad chunk) -> row-contiguous atomics
-      double* os = reinterpret_cast<double*>(st_out + lane * (S::OUT_STRIDE * 16));
-      int64_t* orow = reinterpret_cast<int64_t*>(st_out + (lane * S::OUT_STRIDE + S::RC) * 16);
+      double* os = reinterpret_cast<double*>(st_out + lane * (S::out_stride(2) * 16));
+      int64_t* orow = reinterpret_cast<int64_t*>(st_out + (lane * S::out_stride(2) + S::RC) * 16);
       store_full<N, REG>(os, g1r);
       if (KIND != kSpd) store_full<N, REG>(os + N * N, g1i);
       *orow = active ? i1 : -1;

@@ -62,6 +62,54 @@ __global__ void __launch_bounds__(256) scatter_kernel(int64_t total, int per, in
   }
 }
 
+// The same two kernels for the PACKED saved state of the register kernels (state_is_packed): a point's
+// unit gradient is stored as the lower triangles of its symmetric blocks; element c of the full point
+// reads packed entry lut[c] (built once per block in shared memory).
+__device__ __forceinline__ void build_state_lut(short* lut, int per, int n) {
+  const int nn = n * n, tri_n = n * (n + 1) / 2;
+  for (int c = threadIdx.x; c < per; c += blockDim.x) {
+    const int m = c / nn, ij = c - m * nn, i = ij / n, j = ij - i * n;
+    lut[c] = (short)(m * tri_n + (i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) scale_kernel_packed(int64_t total, int per, int per_s, int n,
+                                                           const double* __restrict__ gd, const double* __restrict__ u1,
+                                                           const double* __restrict__ u2, double* __restrict__ o1,
+                                                           double* __restrict__ o2) {
+  __shared__ short lut[2 * SYMPA_MAX_N * SYMPA_MAX_N];
+  build_state_lut(lut, per, n);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t p = e / per;
+    const int c = (int)(e - p * per);
+    const double g = __ldg(gd + p);
+    const int64_t off = p * per_s + lut[c];
+    o1[e] = g * __ldg(u1 + off);
+    o2[e] = g * __ldg(u2 + off);
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel_packed(int64_t total, int per, int per_s, int n, int64_t num_rows,
+                                                             const double* __restrict__ gd, const int64_t* __restrict__ idx,
+                                                             const double* __restrict__ u1, const double* __restrict__ u2,
+                                                             double* __restrict__ grad_table) {
+  __shared__ short lut[2 * SYMPA_MAX_N * SYMPA_MAX_N];
+  build_state_lut(lut, per, n);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t p = e / per;
+    const int c = (int)(e - p * per);
+    const double g = __ldg(gd + p);
+    const int64_t i1 = __ldg(idx + 2 * p), i2 = __ldg(idx + 2 * p + 1);
+    if (i1 < 0 || i1 >= num_rows || i2 < 0 || i2 >= num_rows) continue;
+    const int64_t off = p * per_s + lut[c];
+    atomicAdd(grad_table + i1 * per + c, g * __ldg(u1 + off));
+    atomicAdd(grad_table + i2 * per + c, g * __ldg(u2 + off));
+  }
+}
+
 // grad_w[k] += sum_p grad_dist[p] * vvd[p, k] * (w_k > 0)      (relu backward, metrics.py:118)
 __global__ void __launch_bounds__(256) wsum_grad_kernel(int64_t num_pairs, int n, const double* __restrict__ gd,
                                                         const double* __restrict__ vvd, const double* __restrict__ w,
@@ -216,7 +264,7 @@ const char* sympa_last_cuda_error(void) { return g_last_cuda_error; }
 
 int64_t sympa_workspace_bytes(int kind, int n, int64_t num_pairs) {
   if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N || num_pairs < 0) return -1;
-  return 2 * num_pairs * (int64_t)point_doubles(kind, n) * (int64_t)sizeof(double);
+  return 2 * num_pairs * (int64_t)state_doubles(kind, n) * (int64_t)sizeof(double);
 }
 
 static const int64_t kSplitChunkPairs = 32768;  // scratch per chunk stays L2-resident (n = 10: 134 MB .. n = 5: 35 MB)
@@ -315,7 +363,7 @@ int sympa_dist_forward(int kind, int n, int metric, int64_t num_pairs, const dou
   a.metric = metric;
   if (saved_state != nullptr) {
     a.gz1 = saved_state;
-    a.gz2 = saved_state + num_pairs * (int64_t)point_doubles(kind, n);
+    a.gz2 = saved_state + num_pairs * (int64_t)state_doubles(kind, n);
   }
   setup_scratch(&a, kind, n, scratch, scratch_bytes, false);
   return launch_n(n, kind, saved_state != nullptr ? kModeFwdSave : kModeFwd, a, (cudaStream_t)stream);
@@ -362,11 +410,16 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const do
   if (num_pairs == 0) return SYMPA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int per = point_doubles(kind, n);
+  const int per_s = state_doubles(kind, n);
+  const bool packed = state_is_packed(kind, n);
   const double* u1 = saved_state;
-  const double* u2 = saved_state + num_pairs * (int64_t)per;
+  const double* u2 = saved_state + num_pairs * (int64_t)per_s;
   int rc = SYMPA_OK;
   if (mat) {
-    if (per % 2 == 0) {
+    if (packed) {
+      const int64_t total = num_pairs * (int64_t)per;
+      scale_kernel_packed<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, per_s, n, grad_dist, u1, u2, grad_z1, grad_z2);
+    } else if (per % 2 == 0) {
       const int64_t total2 = num_pairs * (int64_t)(per / 2);
       scale_kernel<<<grid_for(total2, 256, 32), 256, 0, s>>>(total2, per / 2, grad_dist, (const double2*)u1,
                                                              (const double2*)u2, (double2*)grad_z1, (double2*)grad_z2);
@@ -379,7 +432,11 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const do
   }
   if (tab) {
     const int64_t total = num_pairs * (int64_t)per;
-    scatter_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, num_rows, grad_dist, idx, u1, u2, grad_table);
+    if (packed)
+      scatter_kernel_packed<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, per_s, n, num_rows, grad_dist, idx, u1, u2,
+                                                                   grad_table);
+    else
+      scatter_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per, num_rows, grad_dist, idx, u1, u2, grad_table);
     rc = check_launch();
     if (rc) return rc;
   }

@@ -38,8 +38,10 @@ def test_host_only_entry_points(lib):
     assert lib.sympa_error_string(0) == b"ok"
     assert lib.sympa_error_string(2).startswith(b"unsupported")
     # 2 operands * pairs * (2 n n) doubles * 8 bytes
-    assert lib.sympa_workspace_bytes(0, 4, 1000) == 2 * 1000 * 32 * 8
-    assert lib.sympa_workspace_bytes(2, 3, 10) == 2 * 10 * 9 * 8
+    # saved state: packed lower triangles for the register-kernel sizes, full blocks for the cooperative ones
+    assert lib.sympa_workspace_bytes(0, 4, 1000) == 2 * 1000 * 20 * 8
+    assert lib.sympa_workspace_bytes(2, 3, 10) == 2 * 10 * 6 * 8
+    assert lib.sympa_workspace_bytes(0, 10, 10) == 2 * 10 * 200 * 8
     assert lib.sympa_workspace_bytes(0, 11, 10) == -1
     # scratch: only upper n > 4 and batches worth splitting; five n x n planes + n per pair of a chunk, + (1 + n) per pair
     assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 0        # split path is off by default
