@@ -10,7 +10,10 @@
 #ifndef SY_BLOCK_SYNC
 #define SY_BLOCK_SYNC 1
 #endif
-#if defined(SYMPA_PAIR_KERNELS_IMPL) && SY_BLOCK_SYNC
+#ifndef SY_MID_SYNC
+#define SY_MID_SYNC 1
+#endif
+#if defined(SYMPA_PAIR_KERNELS_IMPL) && SY_BLOCK_SYNC && SY_MID_SYNC
 template <int N>
 __host__ __device__ __forceinline__ void sy_phase_sync() {
 #if defined(__CUDA_ARCH__)
