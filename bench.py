@@ -316,6 +316,16 @@ def run_ours(args):
         rec = json.load(open(tpath)).get(f"{kind}_n{n}_fwdsave")
         if rec:
             traffic = rec["bytes_per_pair"] * b     # ncu dram bytes per pair x pairs of one launch
+    scatter = None
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(f"{kind}_n{n}_scatter")
+        if rec:   # the second kernel of a step: its DRAM traffic (ncu) over its live-timed duration
+            sbytes = rec["bytes_per_pair"] * b
+            scatter = {"kernel": "scatter_kernel_packed", "bound": "hbm", "traffic": sbytes,
+                       "achieved": round(sbytes / (bwd * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": round(sbytes / (bwd * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                       "note": "DRAM bytes per pair measured by ncu (random read-modify-write of table-gradient rows that "
+                               "do not fit L2 + the packed saved state), not algorithmic bytes"}
     abytes = algorithmic_bytes_per_pair(kind, n) * b
     achieved = abytes / (fwd * 1e-3) / 1e9
     roofline = {
@@ -331,6 +341,8 @@ def run_ours(args):
         "note": "n >= 3 is bound by the FP64 pipe (Jacobi sweeps), not HBM: see the fp64 object and profiles/; the "
                 "HBM fraction uses algorithmic bytes 64n^2+8n+32 per pair",
     }
+    if scatter is not None:
+        roofline["scatter"] = scatter
     out = {
         "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
