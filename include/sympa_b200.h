@@ -70,11 +70,13 @@ int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
  * geoopt.optim.RiemannianSGD.step for the matrix table - egrad2rgrad (sympa/manifolds/upper_half.py:25-40),
  * retr (siegel_manifold.py:74-87) and projx (upper_half.py:42-66, csym_math.py:252-278) fused per row:
  *   upper:  X <- X - lr Y GX Y,  Y <- clamp_eig(Y - lr Y GY Y, eps) only when an eigenvalue is <= eps
+ *   bounded: Z <- sym(Z - lr A G A), A = I - conj(Z) Z (bounded_domain.py:41-53), then the Takagi values
+ *           above 1 - eps clamped to 1 - eps, only for the rows that have one (bounded_domain.py:55-84;
+ *           what the reference's tests describe - the shipped projx crashes)
  *   spd:    X <- sym(X + U + U X^-1 U / 2),  U = -lr X sym(G) X        (geoopt, parity unpinned)
  * Rows whose gradient is identically zero are not touched (equivalent to the dense step, which leaves
  * them bit-identical).  lr_scale: optional device scalar multiplying lr (a clipping coefficient);
- * projected: optional device counter incremented by the number of rows the projection moved.
- * kind bounded is not offered here (SYMPA_ERR_UNSUPPORTED): use the host-side implementation. */
+ * projected: optional device counter incremented by the number of rows the projection moved. */
 int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
                     const double* lr_scale, unsigned long long* projected, void* stream);
 

@@ -708,7 +708,9 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
       store_full<N, REG>(p, x);
     } else {
       load_packed<N, REG>(p + N * N, y);
-      const bool m = REG ? reg::upper_rsgd_row<N>(x, y, gx, gy, lr) : loc::upper_rsgd_row<N>(x, y, gx, gy, lr);
+      const bool m = (KIND == kBounded)
+                         ? (REG ? reg::bounded_rsgd_row<N>(x, y, gx, gy, lr) : loc::bounded_rsgd_row<N>(x, y, gx, gy, lr))
+                         : (REG ? reg::upper_rsgd_row<N>(x, y, gx, gy, lr) : loc::upper_rsgd_row<N>(x, y, gx, gy, lr));
       moved += m ? 1ull : 0ull;
       store_full<N, REG>(p, x);
       store_full<N, REG>(p + N * N, y);
@@ -724,6 +726,8 @@ int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t s) {
     rsgd_kernel<N, kUpper><<<grid, kThreads, 0, s>>>(a);
   else if (kind == kSpd)
     rsgd_kernel<N, kSpd><<<grid, kThreads, 0, s>>>(a);
+  else if (kind == kBounded)
+    rsgd_kernel<N, kBounded><<<grid, kThreads, 0, s>>>(a);
   else
     return 2;
   return check_launch();

@@ -281,7 +281,7 @@ static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs *
 int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
                     const double* lr_scale, unsigned long long* projected, void* stream) {
   if (n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
-  if (kind != SYMPA_KIND_UPPER && kind != SYMPA_KIND_SPD) return SYMPA_ERR_UNSUPPORTED;
+  if (kind != SYMPA_KIND_UPPER && kind != SYMPA_KIND_SPD && kind != SYMPA_KIND_BOUNDED) return SYMPA_ERR_UNSUPPORTED;
   if (num_rows < 0 || table == nullptr || grad == nullptr) return SYMPA_ERR_BAD_ARG;
   if (num_rows == 0) return SYMPA_OK;
   RsgdArgs a = {};

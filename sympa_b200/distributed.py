@@ -65,3 +65,68 @@ def allreduce_gradients(tensors, average=True):
         if average and not fused_avg:
             t.div_(world)
     return tensors
+
+
+def row_shard(num_rows, rank, world):
+    """Rows [begin, end) of the table owned by `rank`: equal blocks of ceil(N / world) rows (the last
+    block may be shorter or empty)."""
+    per = -(-num_rows // world)
+    begin = min(rank * per, num_rows)
+    return begin, min(begin + per, num_rows), per
+
+
+def sharded_rsgd_step(param, lr, update_rows, average=True):
+    """Owner-computes variant of `allreduce_gradients` + optimizer step for the embedding table
+    (the reference all-reduces the dense gradient through DDP, train.py:59, and
+    every rank then runs the O(N) Riemannian update and projection on the whole table):
+
+      1. reduce-scatter the dense table gradient by row owner (each rank receives the reduced gradient
+         of its ceil(N / world) rows);
+      2. the owner updates its rows:  update_rows(rows_view, grad_rows, lr)  in place - the fused
+         `sympa_b200.ops.rsgd_step` on a GPU, any Riemannian update otherwise;
+      3. all-gather the updated rows into every rank's table.
+
+    Bytes on the wire equal those of the all-reduce (reduce-scatter + all-gather of the same size); what
+    changes is that the update and projection of the table is done once, split over the ranks, instead
+    of world times.  NCCL runs both collectives on the current stream; backends without
+    reduce_scatter_tensor (gloo, CPU tests) take an all-reduce and keep their slice.  Every rank ends
+    with the same table, bit-identical to the replicated step given the same reduced gradient.
+    Returns the (begin, end) rows this rank owns."""
+    table, grad = param.data, param.grad
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        update_rows(table, grad, lr)
+        return 0, table.shape[0]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_rows = table.shape[0]
+    begin, end, per = row_shard(n_rows, rank, world)
+    row_elems = table[0].numel()
+    padded = per * world
+    nccl = dist.get_backend() == "nccl"
+    if nccl:
+        src = grad.reshape(n_rows, row_elems)
+        if padded != n_rows:   # reduce_scatter_tensor wants world equal blocks
+            src = torch.cat([src, src.new_zeros(padded - n_rows, row_elems)])
+        mine = torch.empty(per, row_elems, dtype=grad.dtype, device=grad.device)
+        dist.reduce_scatter_tensor(mine, src, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM)
+        mine = mine[: end - begin]
+    else:
+        full = grad.clone()
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)
+        if average:
+            full.div_(world)
+        mine = full.reshape(n_rows, row_elems)[begin:end]
+    if end > begin:
+        update_rows(table[begin:end], mine.reshape((end - begin,) + tuple(table.shape[1:])), lr)
+    # all-gather the updated rows
+    block = torch.zeros(per, row_elems, dtype=table.dtype, device=table.device)
+    if end > begin:
+        block[: end - begin] = table[begin:end].reshape(end - begin, row_elems)
+    if nccl:
+        gathered = torch.empty(padded, row_elems, dtype=table.dtype, device=table.device)
+        dist.all_gather_into_tensor(gathered, block)
+    else:
+        parts = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(parts, block)
+        gathered = torch.cat(parts)
+    table.copy_(gathered[:n_rows].reshape(table.shape))
+    return begin, end

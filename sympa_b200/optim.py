@@ -13,7 +13,7 @@ import torch
 
 class RiemannianSGD(torch.optim.Optimizer):
     def __init__(self, params, lr, weight_decay=0.0, sparse_rows=False, fused=False):
-        """fused=True: CUDA tables on the upper / spd manifolds are updated by the one-launch kernel
+        """fused=True: CUDA tables on the upper / bounded / spd manifolds are updated by the one-launch kernel
         behind sympa_rsgd_step (rows with a zero gradient untouched); everything else takes the torch
         path below."""
         super().__init__(params, dict(lr=lr, weight_decay=weight_decay, sparse_rows=sparse_rows, fused=fused))
@@ -37,10 +37,10 @@ class RiemannianSGD(torch.optim.Optimizer):
                     p.add_(g, alpha=-lr)
                     continue
                 kind = getattr(manifold, "kind", None)
-                if group["fused"] and wd == 0.0 and p.is_cuda and kind in ("upper", "spd") and p.dtype == torch.float64:
+                if group["fused"] and wd == 0.0 and p.is_cuda and kind in ("upper", "bounded", "spd") and p.dtype == torch.float64:
                     from . import ops
                     counter = None
-                    if kind == "upper":
+                    if kind in ("upper", "bounded"):
                         counter = getattr(manifold, "_projected_counter", None)
                         if counter is None or counter.device != p.device:
                             counter = torch.zeros(1, dtype=torch.int64, device=p.device)

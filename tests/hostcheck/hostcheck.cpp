@@ -219,7 +219,8 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
         NS::pack_sym<N>(p + N * N, y);                                                                       \
         NS::pack_sym<N>(g, gx);                                                                              \
         NS::pack_sym<N>(g + N * N, gy);                                                                      \
-        projected += NS::upper_rsgd_row<N>(x, y, gx, gy, lr) ? 1 : 0;                                        \
+        projected += (kind == kBounded ? NS::bounded_rsgd_row<N>(x, y, gx, gy, lr)                           \
+                                       : NS::upper_rsgd_row<N>(x, y, gx, gy, lr)) ? 1 : 0;                    \
         for (int i = 0; i < N; ++i)                                                                          \
           for (int j = 0; j < N; ++j) {                                                                      \
             p[i * N + j] = x[tri(i, j)];                                                                     \
@@ -234,7 +235,6 @@ HC_RSGD(loc)
 
 extern "C" int64_t hostcheck_rsgd(int variant, int kind, int n, int64_t rows, double* table, const double* grad,
                                   double lr) {
-  if (kind == kBounded) return -1;
   if (variant == 0) {
     switch (n) {
 #define CASE(K) case K: return rsgd_reg<K>(kind, rows, table, grad, lr);

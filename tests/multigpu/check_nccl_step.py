@@ -1,0 +1,67 @@
+"""Multi-GPU (NCCL) check of the data-parallel step; run under torchrun on >= 2 GPUs, e.g.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu/check_nccl_step.py
+(not collected by pytest: the -m gpu suite runs on one GPU; the same logic is covered on CPU with gloo in
+tests/test_distributed_gloo.py).  Checks, on every rank:
+  * pairs sharded over the ranks + the averaged NCCL all-reduce of the table gradient == the full-batch
+    gradient of one GPU / world;
+  * the owner-computes optimizer step (reduce-scatter, fused sympa_rsgd_step on the owned rows,
+    all-gather) leaves every rank with the table of the replicated step."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import siegel_oracle as so
+    from sympa_b200 import MetricType, UpperHalfManifold, ops
+    from sympa_b200 import distributed as sd
+    from sympa_b200.embeddings import ManifoldParameter
+
+    rank, world, local = sd.init_process_group()
+    dev = torch.device("cuda", local)
+    g = torch.Generator().manual_seed(0)
+    rows, pairs, n = 1001, 40000, 4
+    table = so.upper_spread(rows, n, generator=g, scale=0.3).to(dev)
+    src = torch.randint(0, rows, (pairs,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (pairs,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).to(dev)
+    gd = torch.randint(1, 20, (pairs,), generator=g).double().to(dev)
+    man = UpperHalfManifold(dims=n, metric=MetricType.from_str("riem")).to(dev)
+
+    def grad_of(sel):
+        t = table.clone().requires_grad_(True)
+        d = man.dist_from_table(t, idx[sel].contiguous())
+        (torch.abs((d / gd[sel]) ** 2 - 1)).sum().backward()
+        return t.grad
+
+    shard = sd.shard_indices(pairs, rank, world, shuffle=True, seed=0, drop_last=True).to(dev)
+    local_grad = grad_of(shard)
+    (avg,) = sd.allreduce_gradients([local_grad.clone()], average=True)
+    all_sel = torch.cat([sd.shard_indices(pairs, k, world, shuffle=True, seed=0, drop_last=True) for k in range(world)]).to(dev)
+    full = grad_of(all_sel)
+    torch.testing.assert_close(avg * world, full, rtol=1e-9, atol=1e-9 * full.abs().max().item())
+
+    lr = 0.05
+    rep = table.clone()
+    ops.rsgd_step("upper", rep, avg, lr)
+    p = ManifoldParameter(table.clone(), manifold=man)
+    p.grad = local_grad.clone()
+    begin, end = sd.sharded_rsgd_step(p, lr, lambda t, gr, step: ops.rsgd_step("upper", t, gr.contiguous(), step))
+    assert (begin, end) == sd.row_shard(rows, rank, world)[:2]
+    # the reduce-scatter and the all-reduce may sum in different orders: equal up to rounding
+    torch.testing.assert_close(p.data, rep, rtol=1e-12, atol=1e-13)
+    ops.check_status(dev)
+    dist.barrier()
+    if rank == 0:
+        print(f"nccl step check ok on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

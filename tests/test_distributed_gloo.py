@@ -65,3 +65,48 @@ def test_two_rank_gradient_allreduce_matches_full_batch():
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _worker_sharded(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import siegel_oracle as so
+    from sympa_b200 import UpperHalfManifold
+    from sympa_b200 import distributed as sd
+    from sympa_b200.embeddings import ManifoldParameter
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sd.init_process_group(backend="gloo")
+    g = torch.Generator().manual_seed(1)
+    rows, n, lr = 23, 3, 0.3                      # 23 rows over 2 ranks: blocks of 12 and 11
+    table = so.upper_spread(rows, n, generator=g, scale=0.3)
+    grads = [so.sym(torch.randn(rows, 2, n, n, dtype=torch.float64, generator=g)) for _ in range(world)]
+    man = UpperHalfManifold(dims=n)
+
+    def update_rows(t, gr, step):              # the Riemannian update of the host optimizer, in place
+        t.copy_(man.retr(t, -step * man.egrad2rgrad(t, gr)))
+
+    # replicated step: all-reduce (average) then update the whole table on every rank
+    rep = table.clone()
+    (avg,) = sd.allreduce_gradients([grads[rank].clone()], average=True)
+    update_rows(rep, avg, lr)
+    # owner-computes step
+    p = ManifoldParameter(table.clone(), manifold=man)
+    p.grad = grads[rank].clone()
+    begin, end = sd.sharded_rsgd_step(p, lr, update_rows, average=True)
+    ok = (begin, end) == sd.row_shard(rows, rank, world)[:2]
+    ok = ok and torch.equal(p.data, rep)
+    ok = ok and torch.allclose(rep, so.rsgd_step("upper", table, sum(grads) / world, lr), rtol=1e-10, atol=1e-12)
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_optimizer_step_equals_replicated_step():
+    world = 2
+    port = 29900 + os.getpid() % 90
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker_sharded, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}

@@ -92,3 +92,24 @@ def test_row_update_templates_match_oracle_spd(hostcheck, n):
     for variant in ((0, 1) if n <= 6 else (1,)):
         out, _ = hostcheck.rsgd(variant, "spd", n, x.numpy(), gr.numpy(), lr)
         torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 10])
+@pytest.mark.parametrize("lr", [1e-2, 5.0])
+def test_row_update_templates_match_oracle_bounded(hostcheck, n, lr):
+    """bounded-domain row update behind sympa_rsgd_step (A G A with A = I - conj(Z) Z, then the Takagi values
+    above 1 - eps clamped) against the oracle's restatement of bounded_domain.py:41-84 (projx with a
+    factoriser that returns eigenvectors)."""
+    table, grad, touched = make("bounded", 40, n, 21 + n)
+    ref = so.rsgd_step("bounded", table, grad, lr)
+    moved_ref = int((~torch.isclose(ref, so.to_symmetric(table - lr * so.bounded_egrad2rgrad(table, grad)), rtol=0, atol=1e-13)
+                     .reshape(len(table), -1).all(dim=1)).sum())
+    for variant in ((0, 1) if n <= 6 else (1,)):
+        out, projected = hostcheck.rsgd(variant, "bounded", n, table.numpy(), grad.numpy(), lr)
+        torch.testing.assert_close(torch.from_numpy(out), ref, rtol=1e-9, atol=1e-11)
+        assert projected == moved_ref
+        if lr > 1:
+            assert projected > 0
+        man = BoundedDomainManifold(dims=n)
+        for i in range(len(table)):
+            assert man.check_point_on_manifold(torch.from_numpy(out[i]))

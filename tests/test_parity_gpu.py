@@ -322,7 +322,8 @@ def test_train_epoch_matches_oracle_loop(sb, kind, metric, n):
     torch.testing.assert_close(model.embeddings.embeds.detach().cpu(), table, rtol=1e-6, atol=1e-9)
 
 
-@pytest.mark.parametrize("kind,n", [("upper", 2), ("upper", 3), ("upper", 4), ("upper", 6), ("upper", 10), ("spd", 3), ("spd", 6)])
+@pytest.mark.parametrize("kind,n", [("upper", 2), ("upper", 3), ("upper", 4), ("upper", 6), ("upper", 10), ("spd", 3), ("spd", 6),
+                                    ("bounded", 2), ("bounded", 3), ("bounded", 4), ("bounded", 7), ("bounded", 10)])
 @pytest.mark.parametrize("lr", [1e-2, 5.0])
 def test_fused_rsgd_step_matches_host_optimizer(sb, kind, n, lr):
     """sympa_rsgd_step (one launch: egrad2rgrad + retr + projx per row) against the torch implementation
@@ -338,6 +339,9 @@ def test_fused_rsgd_step_matches_host_optimizer(sb, kind, n, lr):
     else:
         table = so.upper_spread(rows, n, generator=g, scale=0.3)
         man = sb.UpperHalfManifold(dims=n)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+            man = sb.BoundedDomainManifold(dims=n)
     grad = torch.zeros_like(table)
     touched = torch.randperm(rows, generator=g)[: rows // 3]
     gr = torch.randn((len(touched),) + tuple(table.shape[1:]), dtype=torch.float64, generator=g)
@@ -352,8 +356,8 @@ def test_fused_rsgd_step_matches_host_optimizer(sb, kind, n, lr):
     untouched = torch.ones(rows, dtype=torch.bool)
     untouched[touched] = False
     assert torch.equal(out[True][untouched], table[untouched])
-    if kind == "upper":
-        torch.testing.assert_close(out[True], so.rsgd_step("upper", table, grad, lr), rtol=1e-9, atol=1e-11)
+    if kind in ("upper", "bounded"):
+        torch.testing.assert_close(out[True], so.rsgd_step(kind, table, grad, lr), rtol=1e-9, atol=1e-11)
         if lr > 1:
             assert man.projected_points > 0
 
