@@ -262,13 +262,15 @@ def run_ours(args):
                                             wsum_w=None, want_grad=True)
             ev[1].record()
         g = torch.ones_like(dd)
-        gt = torch.zeros_like(table)
+        gt = torch.empty_like(table)
         from sympa_b200 import _lib
         lib = _lib.load()
-        ev[2].record()
-        _lib.check(lib.sympa_dist_backward(_lib.KIND[kind], n, _lib.METRIC["riem"], b, g.data_ptr(), saved.data_ptr(),
-                                           None, None, gt.data_ptr(), rows, idx.data_ptr(), None, None, None,
-                                           torch.cuda.current_stream().cuda_stream))
+        ws, ws_bytes = ops.backward_workspace_for(kind, n, rows, dev)
+        ev[2].record()   # the backward of the table path as the autograd Function issues it (workspace, overwrite)
+        _lib.check(lib.sympa_dist_backward_table(_lib.KIND[kind], n, _lib.METRIC["riem"], b, g.data_ptr(), saved.data_ptr(),
+                                                 gt.data_ptr(), rows, idx.data_ptr(), None, None, None,
+                                                 None if ws is None else ws.data_ptr(), ws_bytes, 1,
+                                                 torch.cuda.current_stream().cuda_stream))
         ev[3].record()
         torch.cuda.synchronize()
         fwd_ms.append(ev[0].elapsed_time(ev[1]))
@@ -321,7 +323,7 @@ def run_ours(args):
         rec = json.load(open(tpath)).get(f"{kind}_n{n}_scatter")
         if rec:   # the second kernel of a step: its DRAM traffic (ncu) over its live-timed duration
             sbytes = rec["bytes_per_pair"] * b
-            scatter = {"kernel": "scatter_kernel_packed", "bound": "hbm", "traffic": sbytes,
+            scatter = {"kernel": rec.get("kernel", "scatter kernel"), "bound": "hbm", "traffic": sbytes,
                        "achieved": round(sbytes / (bwd * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": round(sbytes / (bwd * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                        "note": "DRAM bytes per pair measured by ncu (random read-modify-write of table-gradient rows that "
@@ -410,18 +412,24 @@ def quick_pairs_per_s(kind, n, metric, pairs, rows, dev, world, steps=5):
     return world * pairs * steps / (ms * 1e-3)
 
 
-def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True):
-    """BASELINE config 1: grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2, batch 2048,
-    RiemannianSGD - seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept)."""
+def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, config=1):
+    """Seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept), batch 2048, RiemannianSGD.
+    config 1 (BASELINE configs[0]): grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2;
+    config 2 (BASELINE configs[1]): balanced tree branching 3 height 5 (364 nodes, 66 066 pairs), bounded / fone / n=3."""
     from types import SimpleNamespace
-    from sympa_b200.graphs import grid_triplets
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
     from sympa_b200.model import Model
     from sympa_b200.optim import RiemannianSGD
     from sympa_b200.runner import train_epoch
     torch.manual_seed(0)
-    idx, gd, nodes = grid_triplets(20, 2)
-    args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
-                           train_scale=False)
+    if config == 1:
+        idx, gd, nodes = grid_triplets(20, 2)
+        args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                               train_scale=False)
+    else:
+        idx, gd, nodes = balanced_tree_triplets(3, 5)
+        args = SimpleNamespace(manifold="bounded", metric="fone", dims=3, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                               train_scale=False)
     model = Model(args).to(dev)
     opt = RiemannianSGD(model.parameters(), lr=1e-2 * world, fused=fused)
     idx, gd = idx.to(dev), gd.to(dev)
@@ -449,6 +457,9 @@ def extras(args, world, rank, dev):
         out["train_epoch_sec_config1_host_optimizer"] = sec_h
         sec_n, _ = epoch_seconds(dev, world, rank, fused=True, sync_stats=False)
         out["train_epoch_sec_config1_no_per_step_item_sync"] = sec_n
+        sec2, loss2 = epoch_seconds(dev, world, rank, fused=True, sync_stats=True, config=2)
+        out["train_epoch_sec_config2_tree_b3h5_bounded_fone_n3_b2048"] = sec2
+        out["train_epoch_config2_final_loss"] = loss2
     except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -129,6 +129,20 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs,
                         const double* vvd, const double* wsum_w, double* grad_wsum_w,
                         void* stream);
 
+/* Table-gradient backward with an optional workspace (same result as sympa_dist_backward in its table
+ * form).  workspace: sympa_backward_workspace_bytes(kind, n, num_rows) bytes of device memory (contents
+ * irrelevant; 0 = this configuration does not use one).  When given and the batch covers the table
+ * densely (2 * num_pairs >= num_rows) the scatter-add runs on a packed (lower-triangle) gradient table in
+ * the workspace and the dense symmetric rows are produced in one pass at the end; otherwise the direct
+ * scatter is used.  overwrite != 0: grad_table is WRITTEN (the caller need not zero it - what an autograd
+ * backward wants for its freshly allocated gradient); overwrite == 0: accumulated into, as above. */
+int64_t sympa_backward_workspace_bytes(int kind, int n, int64_t num_rows);
+int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs,
+                              const double* grad_dist, const double* saved_state,
+                              double* grad_table, int64_t num_rows, const int64_t* idx,
+                              const double* vvd, const double* wsum_w, double* grad_wsum_w,
+                              double* workspace, int64_t workspace_bytes, int overwrite, void* stream);
+
 /* One fused launch for a training step of the distortion objective (sympa/losses.py:16-19 with
  * the scale of sympa/model.py:30):   L = sum_p | (scale * dist_p / graph_dist_p)^2 - 1 |.
  * Gathers both rows, computes dist, the loss term and its derivative, and scatter-adds

@@ -32,6 +32,8 @@ EXPORTS = (
     "sympa_dist_backward",
     "sympa_distortion_step",
     "sympa_dist_matrix",
+    "sympa_backward_workspace_bytes",
+    "sympa_dist_backward_table",
 )
 
 _lib = None
@@ -73,6 +75,10 @@ def load():
     lib.sympa_distortion_step.argtypes = [I, I, I, L, P, L, P, P, D, P, P, P, P, P, P, P, L, P, P]
     lib.sympa_dist_matrix.restype = I
     lib.sympa_dist_matrix.argtypes = [I, I, I, P, L, L, L, P, P, P, L, P, P]
+    lib.sympa_backward_workspace_bytes.restype = L
+    lib.sympa_backward_workspace_bytes.argtypes = [I, I, L]
+    lib.sympa_dist_backward_table.restype = I
+    lib.sympa_dist_backward_table.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, L, I, P]
     _lib = lib
     return lib
 

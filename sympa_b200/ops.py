@@ -43,6 +43,23 @@ def scratch_for(kind, n, num_pairs, device):
     return buf, buf.numel() * 8
 
 
+_bwd_workspace = {}
+
+
+def backward_workspace_for(kind, n, num_rows, device):
+    """Per-device workspace of the table-gradient backward (packed gradient table; grown on demand and
+    reused - calls are stream-ordered)."""
+    nbytes = _lib.load().sympa_backward_workspace_bytes(_lib.KIND[kind], n, num_rows)
+    if nbytes <= 0:
+        return None, 0
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _bwd_workspace.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        _bwd_workspace[key] = buf
+    return buf, buf.numel() * 8
+
+
 def check_status(device=None, reset=True):
     """Host-synchronising check of the device status word (call once per step / epoch; the
     reference asserted synchronously inside every dist call, siegel_manifold.py:65-66)."""
@@ -188,15 +205,17 @@ class _TableDistFn(torch.autograd.Function):
             return (torch.zeros(ctx.tshape, dtype=torch.float64, device=dev), None,
                     (None if wsum_w is None else torch.zeros_like(wsum_w)), None, None)
         with torch.cuda.device(dev):
-            gt = torch.zeros(ctx.tshape, dtype=torch.float64, device=dev)
+            gt = torch.empty(ctx.tshape, dtype=torch.float64, device=dev)     # written, not accumulated (overwrite=1)
             gw = None
             w_flat = None
             if wsum_w is not None and ctx.needs_input_grad[2]:
                 gw = torch.zeros(n, dtype=torch.float64, device=dev)
                 w_flat = wsum_w.contiguous().reshape(-1)
-            _lib.check(lib.sympa_dist_backward(
-                _lib.KIND[ctx.kind], n, _lib.METRIC[ctx.metric], b, _ptr(grad_dist), _ptr(saved), None, None,
-                _ptr(gt), ctx.tshape[0], _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat), _ptr(gw), _stream()))
+            ws, ws_bytes = backward_workspace_for(ctx.kind, n, ctx.tshape[0], dev)
+            _lib.check(lib.sympa_dist_backward_table(
+                _lib.KIND[ctx.kind], n, _lib.METRIC[ctx.metric], b, _ptr(grad_dist), _ptr(saved),
+                _ptr(gt), ctx.tshape[0], _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat), _ptr(gw),
+                _ptr(ws), ws_bytes, 1, _stream()))
         if gw is not None:
             gw = gw.reshape(wsum_w.shape)
         return gt, None, gw, None, None

@@ -451,3 +451,50 @@ def test_distance_matrix_matches_oracle_and_reference_semantics(sb, kind, n, met
     assert torch.equal(block, full[5:14])
     assert man.dist_matrix(t, 3, 0).shape == (0, rows)
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 4), ("bounded", 3), ("spd", 5), ("upper", 8)])
+@pytest.mark.parametrize("pairs", [7, 400])
+def test_table_backward_with_workspace_equals_direct_scatter(sb, kind, n, pairs):
+    """sympa_dist_backward_table (packed gradient table in a workspace + one expansion pass when the batch
+    covers the table densely; overwrite / accumulate) against the direct scatter of sympa_dist_backward."""
+    from sympa_b200 import _lib
+    lib = _lib.load()
+    rows = 60
+    g = torch.Generator().manual_seed(3 + n)
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g).cuda()
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+        table = table.cuda()
+    src = torch.randint(0, rows, (pairs,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (pairs,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    idx[min(3, pairs - 1), 1] = rows + 5         # one rejected pair: contributes nothing
+    gdist = torch.randn(pairs, generator=g, dtype=torch.float64).cuda()
+    _, _, saved = sb.ops.forward_raw(kind, "riem", table=table, idx=idx, want_grad=True)
+    sb.ops.status_word(table.device).zero_()     # the rejected pair raised the bad-index bit on purpose
+    k, stream = _lib.KIND[kind], torch.cuda.current_stream().cuda_stream
+    ref = torch.zeros_like(table)
+    _lib.check(lib.sympa_dist_backward(k, n, 0, pairs, gdist.data_ptr(), saved.data_ptr(), None, None, ref.data_ptr(),
+                                       rows, idx.data_ptr(), None, None, None, stream))
+    ws, ws_bytes = sb.ops.backward_workspace_for(kind, n, rows, table.device)
+    assert (ws is None) == (lib.sympa_backward_workspace_bytes(k, n, rows) == 0)
+    out = torch.full_like(table, float("nan"))   # overwrite mode must not read it
+    _lib.check(lib.sympa_dist_backward_table(k, n, 0, pairs, gdist.data_ptr(), saved.data_ptr(), out.data_ptr(), rows,
+                                             idx.data_ptr(), None, None, None, None if ws is None else ws.data_ptr(),
+                                             ws_bytes, 1, stream))
+    tol = 1e-12 * ref.abs().max().item()
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=tol)
+    acc = ref.clone()                            # accumulate mode: 2 x ref
+    _lib.check(lib.sympa_dist_backward_table(k, n, 0, pairs, gdist.data_ptr(), saved.data_ptr(), acc.data_ptr(), rows,
+                                             idx.data_ptr(), None, None, None, None if ws is None else ws.data_ptr(),
+                                             ws_bytes, 0, stream))
+    torch.testing.assert_close(acc, 2 * ref, rtol=1e-12, atol=2 * tol)
+    # symmetric rows: exactly for the packed route (both triangles come from one accumulator), up to the
+    # order of the atomics for the direct scatter
+    torch.testing.assert_close(out, out.transpose(-1, -2), rtol=0, atol=tol)
+    if ws is not None and 2 * pairs >= rows:
+        assert torch.equal(out, out.transpose(-1, -2))
