@@ -320,14 +320,16 @@ def run_ours(args):
             traffic = rec["bytes_per_pair"] * b     # ncu dram bytes per pair x pairs of one launch
     scatter = None
     if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(f"{kind}_n{n}_scatter")
-        if rec:   # the second kernel of a step: its DRAM traffic (ncu) over its live-timed duration
-            sbytes = rec["bytes_per_pair"] * b
-            scatter = {"kernel": rec.get("kernel", "scatter kernel"), "bound": "hbm", "traffic": sbytes,
+        rec = json.load(open(tpath)).get(f"{kind}_n{n}_backward")
+        if rec:   # the backward of a step: its DRAM traffic (ncu) over its live-timed duration
+            sbytes = rec["scatter_bytes_per_pair"] * b + rec["expand_bytes_per_row"] * rows
+            scatter = {"kernel": rec["kernel"], "bound": "hbm", "traffic": sbytes,
                        "achieved": round(sbytes / (bwd * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": round(sbytes / (bwd * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                       "note": "DRAM bytes per pair measured by ncu (random read-modify-write of table-gradient rows that "
-                               "do not fit L2 + the packed saved state), not algorithmic bytes"}
+                       "note": "DRAM bytes measured by ncu at 2^20 pairs / 2^20 rows (per pair: random read-modify-write of "
+                               "packed table-gradient rows that do not fit L2 + the packed saved state; per row: memset, "
+                               "read and dense write of the expansion), scaled to this run's pairs and rows - not "
+                               "algorithmic bytes"}
     abytes = algorithmic_bytes_per_pair(kind, n) * b
     achieved = abytes / (fwd * 1e-3) / 1e9
     roofline = {
