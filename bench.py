@@ -444,6 +444,34 @@ def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, confi
     return (time.perf_counter() - t0) / epochs, loss
 
 
+def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
+    """The same epochs on sympa_b200.runner.FusedEpochRunner: two launches per step (fused distortion step, fused
+    optimizer row kernel with clipping and zero_grad), the epoch replayed from a CUDA graph on one GPU, the loss
+    read back once per epoch."""
+    from types import SimpleNamespace
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
+    from sympa_b200.model import Model
+    from sympa_b200.runner import FusedEpochRunner
+    torch.manual_seed(0)
+    if config == 1:
+        idx, gd, nodes = grid_triplets(20, 2)
+        args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                               train_scale=False)
+    else:
+        idx, gd, nodes = balanced_tree_triplets(3, 5)
+        args = SimpleNamespace(manifold="bounded", metric="fone", dims=3, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                               train_scale=False)
+    model = Model(args).to(dev)
+    runner = FusedEpochRunner(model, 1e-2 * world, idx.to(dev), gd.to(dev), 2048, world_size=world, rank=rank)
+    runner.run_epoch(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for ep in range(1, epochs + 1):
+        loss = runner.run_epoch(ep)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / epochs, loss
+
+
 def extras(args, world, rank, dev):
     """The other sizes BASELINE.json's metric names (n = 10) and its epoch-time leg, measured briefly."""
     out = {}
@@ -459,6 +487,10 @@ def extras(args, world, rank, dev):
         out["train_epoch_sec_config1_host_optimizer"] = sec_h
         sec_n, _ = epoch_seconds(dev, world, rank, fused=True, sync_stats=False)
         out["train_epoch_sec_config1_no_per_step_item_sync"] = sec_n
+        for cfg, key in ((1, "train_epoch_sec_config1_fused_graph"), (2, "train_epoch_sec_config2_fused_graph")):
+            sec_g, loss_g = fused_epoch_seconds(dev, world, rank, config=cfg)
+            out[key] = sec_g
+            out[key.replace("_sec_", "_final_loss_")] = loss_g
         sec2, loss2 = epoch_seconds(dev, world, rank, fused=True, sync_stats=True, config=2)
         out["train_epoch_sec_config2_tree_b3h5_bounded_fone_n3_b2048"] = sec2
         out["train_epoch_config2_final_loss"] = loss2

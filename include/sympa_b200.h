@@ -79,6 +79,11 @@ int64_t sympa_scratch_bytes(int kind, int n, int64_t num_pairs);
  * projected: optional device counter incremented by the number of rows the projection moved. */
 int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
                     const double* lr_scale, unsigned long long* projected, void* stream);
+/* The same with optimizer.zero_grad() (runner.py:117-118) fused in: zero_grad != 0 zeroes the gradient rows
+ * that were applied (rows that were already zero are not touched), so that a training step on the fused
+ * path is two launches: sympa_distortion_step and this. */
+int sympa_rsgd_step_ex(int kind, int n, int64_t num_rows, double* table, double* grad, double lr,
+                       const double* lr_scale, unsigned long long* projected, int zero_grad, void* stream);
 
 /* process-wide tuning switches (host side only).  SYMPA_OPT_SPLIT_PATH: 0 (default) = larger matrix
  * sizes run as ONE cooperative kernel; 1 = three kernels through `scratch` (sympa_scratch_bytes then

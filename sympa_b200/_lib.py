@@ -26,6 +26,7 @@ EXPORTS = (
     "sympa_workspace_bytes",
     "sympa_scratch_bytes",
     "sympa_rsgd_step",
+    "sympa_rsgd_step_ex",
     "sympa_set_option",
     "sympa_probe_fp64",
     "sympa_dist_forward",
@@ -61,6 +62,8 @@ def load():
     lib.sympa_workspace_bytes.argtypes = [I, I, L]
     lib.sympa_rsgd_step.restype = I
     lib.sympa_rsgd_step.argtypes = [I, I, L, P, P, D, P, P, P]
+    lib.sympa_rsgd_step_ex.restype = I
+    lib.sympa_rsgd_step_ex.argtypes = [I, I, L, P, P, D, P, P, I, P]
     lib.sympa_probe_fp64.restype = L
     lib.sympa_probe_fp64.argtypes = [I, P, P]
     lib.sympa_set_option.restype = I

@@ -65,6 +65,7 @@ struct RsgdArgs {
   double lr;
   const double* lr_scale;           // optional device scalar multiplying lr (e.g. a clipping coefficient)
   unsigned long long* projected;    // optional device counter of rows the projection had to move
+  int zero_grad;                    // != 0: the gradient rows that were applied are zeroed (fused zero_grad)
 };
 
 // launch the optimizer-row kernel for matrix size N; defined in pair_kernels_n.cu
@@ -701,6 +702,11 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
 #pragma unroll
     for (int i = 0; i < T; ++i) any = any || (gx[i] != 0.0) || (KIND != kSpd && gy[i] != 0.0);
     if (!any) continue;
+    if (a.zero_grad) {  // the caller owns the gradient buffer and asked for optimizer.zero_grad() in the same pass
+      double* gw = const_cast<double*>(g);
+#pragma unroll 4
+      for (int e = 0; e < PER; ++e) gw[e] = 0.0;
+    }
     double x[T], y[T];
     load_packed<N, REG>(p, x);
     if (KIND == kSpd) {

@@ -137,6 +137,23 @@ __global__ void __launch_bounds__(256) expand_table_kernel(int64_t total, int pe
   __shared__ short lut[2 * SYMPA_MAX_N * SYMPA_MAX_N];
   build_state_lut(lut, per, n);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (per % 2 == 0) {  // two consecutive elements of a row per thread: 16-byte stores
+    double2* gt2 = reinterpret_cast<double2*>(grad_table);
+    const int per2 = per / 2;
+    for (int64_t e2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e2 < total / 2; e2 += stride) {
+      const int64_t r = e2 / per2;
+      const int c = 2 * (int)(e2 - r * per2);
+      const double* row = ws + r * per_s;
+      double2 v = make_double2(__ldg(row + lut[c]), __ldg(row + lut[c + 1]));
+      if (!overwrite) {
+        const double2 o = gt2[e2];
+        v.x += o.x;
+        v.y += o.y;
+      }
+      gt2[e2] = v;
+    }
+    return;
+  }
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t r = e / per;
     const int c = (int)(e - r * per);
@@ -315,6 +332,11 @@ static int64_t scratch_tail_bytes(int n, int64_t num_pairs) { return num_pairs *
 
 int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const double* grad, double lr,
                     const double* lr_scale, unsigned long long* projected, void* stream) {
+  return sympa_rsgd_step_ex(kind, n, num_rows, table, const_cast<double*>(grad), lr, lr_scale, projected, 0, stream);
+}
+
+int sympa_rsgd_step_ex(int kind, int n, int64_t num_rows, double* table, double* grad, double lr,
+                       const double* lr_scale, unsigned long long* projected, int zero_grad, void* stream) {
   if (n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
   if (kind != SYMPA_KIND_UPPER && kind != SYMPA_KIND_SPD && kind != SYMPA_KIND_BOUNDED) return SYMPA_ERR_UNSUPPORTED;
   if (num_rows < 0 || table == nullptr || grad == nullptr) return SYMPA_ERR_BAD_ARG;
@@ -326,6 +348,7 @@ int sympa_rsgd_step(int kind, int n, int64_t num_rows, double* table, const doub
   a.lr = lr;
   a.lr_scale = lr_scale;
   a.projected = projected;
+  a.zero_grad = zero_grad;
   return launch_rsgd_n(n, kind, a, (cudaStream_t)stream);
 }
 
@@ -516,7 +539,8 @@ int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs, co
     if (rc) return rc;
   }
   const int64_t tot = num_rows * (int64_t)per;
-  expand_table_kernel<<<grid_for(tot, 256, 32), 256, 0, s>>>(tot, per, per_s, n, overwrite, workspace, grad_table);
+  expand_table_kernel<<<grid_for(per % 2 == 0 ? tot / 2 : tot, 256, 32), 256, 0, s>>>(tot, per, per_s, n, overwrite, workspace,
+                                                                                    grad_table);
   rc = check_launch();
   if (rc) return rc;
   if (grad_wsum_w != nullptr && metric == SYMPA_METRIC_WSUM && num_pairs > 0) {

@@ -293,8 +293,9 @@ def dist_matrix(kind, metric, table, row_begin=0, row_count=None, wsum_w=None, c
     return out
 
 
-def rsgd_step(kind, table, grad, lr, lr_scale=None, projected=None):
-    """In-place Riemannian SGD update of a CUDA table (one launch); see sympa_rsgd_step in the header."""
+def rsgd_step(kind, table, grad, lr, lr_scale=None, projected=None, zero_grad=False):
+    """In-place Riemannian SGD update of a CUDA table (one launch); see sympa_rsgd_step in the header.
+    zero_grad=True also zeroes the gradient rows it applied."""
     lib = _lib.load()
     if not table.is_cuda or table.dtype != torch.float64 or not table.is_contiguous():
         raise RuntimeError("sympa_b200: rsgd_step needs a contiguous CUDA float64 table (there is no CPU path)")
@@ -302,6 +303,6 @@ def rsgd_step(kind, table, grad, lr, lr_scale=None, projected=None):
     n = table.shape[-1]
     _check_n(n)
     with torch.cuda.device(table.device):
-        _lib.check(lib.sympa_rsgd_step(_lib.KIND[kind], n, table.shape[0], table.data_ptr(), grad.data_ptr(), float(lr),
-                                       _ptr(lr_scale), _ptr(projected), _stream()))
+        _lib.check(lib.sympa_rsgd_step_ex(_lib.KIND[kind], n, table.shape[0], table.data_ptr(), grad.data_ptr(), float(lr),
+                                          _ptr(lr_scale), _ptr(projected), int(bool(zero_grad)), _stream()))
     return table

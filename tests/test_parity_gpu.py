@@ -498,3 +498,34 @@ def test_table_backward_with_workspace_equals_direct_scatter(sb, kind, n, pairs)
     torch.testing.assert_close(out, out.transpose(-1, -2), rtol=0, atol=tol)
     if ws is not None and 2 * pairs >= rows:
         assert torch.equal(out, out.transpose(-1, -2))
+
+
+@pytest.mark.parametrize("manifold,metric,n,use_graph", [("upper", "riem", 2, True), ("bounded", "fone", 3, True),
+                                                         ("upper", "wsum", 3, False), ("spd", "riem", 3, True)])
+def test_fused_epoch_runner_equals_train_epoch(sb, manifold, metric, n, use_graph):
+    """FusedEpochRunner (two launches per step, whole epoch replayed from a CUDA graph) against the step-by-step
+    mirror of runner.py:90-122 with the same permutations, clipping and fused optimizer."""
+    from types import SimpleNamespace
+    from sympa_b200.graphs import balanced_tree_triplets
+    from sympa_b200.model import Model
+    from sympa_b200.optim import RiemannianSGD
+    from sympa_b200.runner import FusedEpochRunner, train_epoch
+    idx, gd, nodes = balanced_tree_triplets(3, 3)
+    idx, gd = idx.cuda(), gd.cuda()
+    args = SimpleNamespace(manifold=manifold, metric=metric, dims=n, num_points=nodes, scale_init=1.0, scale_coef=1.0,
+                           train_scale=False)
+    lr, batch, clip = 5e-2, 128, 3.0           # clip low enough to be active in the first steps
+    torch.manual_seed(2)
+    ref = Model(args).cuda()
+    opt = RiemannianSGD(ref.parameters(), lr=lr, fused=True)
+    ref_losses = [train_epoch(ref, opt, idx, gd, batch, max_grad_norm=clip, epoch=e) for e in range(3)]
+    torch.manual_seed(2)
+    model = Model(args).cuda()
+    runner = FusedEpochRunner(model, lr, idx, gd, batch, max_grad_norm=clip, use_graph=use_graph)
+    losses = [runner.run_epoch(e) for e in range(3)]
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-8)
+    torch.testing.assert_close(model.embeddings.embeds.detach(), ref.embeddings.embeds.detach(), rtol=1e-7, atol=1e-10)
+    if metric == "wsum":
+        torch.testing.assert_close(model.manifold.metric.weights.detach(), ref.manifold.metric.weights.detach(),
+                                   rtol=1e-7, atol=1e-10)
+    assert losses[-1] < losses[0]
