@@ -515,12 +515,17 @@ def test_fused_epoch_runner_equals_train_epoch(sb, manifold, metric, n, use_grap
     args = SimpleNamespace(manifold=manifold, metric=metric, dims=n, num_points=nodes, scale_init=1.0, scale_coef=1.0,
                            train_scale=False)
     lr, batch, clip = 5e-2, 128, 3.0           # clip low enough to be active in the first steps
-    torch.manual_seed(2)
-    ref = Model(args).cuda()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)     # as the reference does (sympa/config.py:17-18): float64 wsum weights
+    try:
+        torch.manual_seed(2)
+        ref = Model(args).cuda()
+        torch.manual_seed(2)
+        model = Model(args).cuda()
+    finally:
+        torch.set_default_dtype(prev)
     opt = RiemannianSGD(ref.parameters(), lr=lr, fused=True)
     ref_losses = [train_epoch(ref, opt, idx, gd, batch, max_grad_norm=clip, epoch=e) for e in range(3)]
-    torch.manual_seed(2)
-    model = Model(args).cuda()
     runner = FusedEpochRunner(model, lr, idx, gd, batch, max_grad_norm=clip, use_graph=use_graph)
     losses = [runner.run_epoch(e) for e in range(3)]
     np.testing.assert_allclose(losses, ref_losses, rtol=1e-8)
