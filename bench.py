@@ -362,7 +362,9 @@ def run_ours(args):
                        "graph distances are copied from pinned host memory (sympa_b200.feeder.PairFeeder: the copy of step "
                        "k+1 overlaps the compute of step k on a side stream; the first copy is exposed), the loss is read "
                        "back and the host waits for it every step"},
-        "gpu_launches": 2 * args.steps,
+        # our kernels per step: forward+unit-gradient kernel, then either the direct scatter (1) or the packed scatter +
+        # expansion (2) - torch's loss / fill kernels are not counted
+        "gpu_launches": (1 + (2 if (ops.backward_workspace_for(kind, n, rows, dev)[1] > 0 and 2 * b >= rows) else 1)) * args.steps,
         "fused_step": {"pairs_per_s": world * b / (ms_fused * 1e-3), "ms_per_step": ms_fused, "launches_per_step": 1},
         "clocks": clocks,
         "roofline": roofline,
