@@ -148,6 +148,22 @@ int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs,
                               const double* vvd, const double* wsum_w, double* grad_wsum_w,
                               double* workspace, int64_t workspace_bytes, int overwrite, void* stream);
 
+/* The two halves of the packed route of sympa_dist_backward_table as separate calls, so that a data-parallel
+ * caller can all-reduce the PACKED gradient table (62 % of the dense bytes at n = 4) between them - the one
+ * collective of the path (DDP's all-reduce of the dense table gradient, train.py:59):
+ *   sympa_table_grad_scatter   workspace <- 0, then scatter-add of grad_dist * unit gradients (packed rows);
+ *                              also dL/dw of the wsum metric when grad_wsum_w is given
+ *   [ncclAllReduce over workspace, sympa_backward_workspace_bytes(kind, n, num_rows) bytes of doubles]
+ *   sympa_table_grad_expand    grad_table <- (or +=) the dense symmetric rows
+ * SYMPA_ERR_UNSUPPORTED for the configurations whose saved state is not packed (workspace size 0). */
+int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs,
+                             const double* grad_dist, const double* saved_state,
+                             int64_t num_rows, const int64_t* idx,
+                             const double* vvd, const double* wsum_w, double* grad_wsum_w,
+                             double* workspace, int64_t workspace_bytes, void* stream);
+int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table,
+                            int overwrite, void* stream);
+
 /* One fused launch for a training step of the distortion objective (sympa/losses.py:16-19 with
  * the scale of sympa/model.py:30):   L = sum_p | (scale * dist_p / graph_dist_p)^2 - 1 |.
  * Gathers both rows, computes dist, the loss term and its derivative, and scatter-adds

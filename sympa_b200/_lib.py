@@ -35,6 +35,8 @@ EXPORTS = (
     "sympa_dist_matrix",
     "sympa_backward_workspace_bytes",
     "sympa_dist_backward_table",
+    "sympa_table_grad_scatter",
+    "sympa_table_grad_expand",
 )
 
 _lib = None
@@ -82,6 +84,10 @@ def load():
     lib.sympa_backward_workspace_bytes.argtypes = [I, I, L]
     lib.sympa_dist_backward_table.restype = I
     lib.sympa_dist_backward_table.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, L, I, P]
+    lib.sympa_table_grad_scatter.restype = I
+    lib.sympa_table_grad_scatter.argtypes = [I, I, I, L, P, P, L, P, P, P, P, P, L, P]
+    lib.sympa_table_grad_expand.restype = I
+    lib.sympa_table_grad_expand.argtypes = [I, I, L, P, P, I, P]
     _lib = lib
     return lib
 

@@ -551,6 +551,46 @@ int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs, co
   return rc;
 }
 
+int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs, const double* grad_dist,
+                             const double* saved_state, int64_t num_rows, const int64_t* idx, const double* vvd,
+                             const double* wsum_w, double* grad_wsum_w, double* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  if (!valid_common(kind, n, metric, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (grad_dist == nullptr || saved_state == nullptr || idx == nullptr || num_rows <= 0) return SYMPA_ERR_BAD_ARG;
+  const int64_t need = sympa_backward_workspace_bytes(kind, n, num_rows);
+  if (need <= 0) return SYMPA_ERR_UNSUPPORTED;   // full-block saved state: use sympa_dist_backward
+  if (workspace == nullptr || workspace_bytes < need) return SYMPA_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int per_s = state_doubles(kind, n);
+  if (cudaMemsetAsync(workspace, 0, (size_t)need, s) != cudaSuccess) return check_launch();
+  int rc = SYMPA_OK;
+  if (num_pairs > 0) {
+    const int64_t total = num_pairs * (int64_t)per_s;
+    scatter_packed_table_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per_s, num_rows, grad_dist, idx, saved_state,
+                                                                       saved_state + num_pairs * (int64_t)per_s, workspace);
+    rc = check_launch();
+    if (rc) return rc;
+    if (grad_wsum_w != nullptr && metric == SYMPA_METRIC_WSUM) {
+      if (vvd == nullptr || wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
+      wsum_grad_kernel<<<grid_for(num_pairs, 256, 4), 256, 0, s>>>(num_pairs, n, grad_dist, vvd, wsum_w, grad_wsum_w);
+      rc = check_launch();
+    }
+  }
+  return rc;
+}
+
+int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table, int overwrite,
+                            void* stream) {
+  if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
+  if (!state_is_packed(kind, n)) return SYMPA_ERR_UNSUPPORTED;
+  if (workspace == nullptr || grad_table == nullptr || num_rows <= 0) return SYMPA_ERR_BAD_ARG;
+  const int per = point_doubles(kind, n);
+  const int64_t tot = num_rows * (int64_t)per;
+  expand_table_kernel<<<grid_for(per % 2 == 0 ? tot / 2 : tot, 256, 32), 256, 0, (cudaStream_t)stream>>>(
+      tot, per, state_doubles(kind, n), n, overwrite, workspace, grad_table);
+  return check_launch();
+}
+
 int sympa_distortion_step(int kind, int n, int metric, int64_t num_pairs, const double* table, int64_t num_rows,
                           const int64_t* idx, const double* graph_dist, double scale, const double* wsum_w,
                           double* grad_table, double* grad_wsum_w, double* grad_scale, double* loss_out,

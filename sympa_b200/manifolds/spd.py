@@ -34,8 +34,8 @@ class SymmetricPositiveDefinite(Manifold):
             _, v, _ = ops.forward_raw("spd", "riem", z1=x, z2=y)
         return v
 
-    def dist_from_table(self, table, idx):
-        d, _ = ops.table_dist("spd", "riem", table, idx)
+    def dist_from_table(self, table, idx, sync_grad=False):
+        d, _ = ops.table_dist("spd", "riem", table, idx, sync_grad=sync_grad)
         return d
 
     def dist_matrix(self, table, row_begin=0, row_count=None):

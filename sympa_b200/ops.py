@@ -186,10 +186,10 @@ class _TableDistFn(torch.autograd.Function):
     atomic scatter-add."""
 
     @staticmethod
-    def forward(ctx, table, idx, wsum_w, kind, metric):
+    def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         dist, vvd, saved = forward_raw(kind, metric, table=table, idx=idx, wsum_w=wsum_w, want_grad=need)
-        ctx.kind, ctx.metric, ctx.tshape = kind, metric, table.shape
+        ctx.kind, ctx.metric, ctx.tshape, ctx.sync_grad = kind, metric, table.shape, sync_grad
         ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None)
         ctx.mark_non_differentiable(vvd)
         return dist, vvd
@@ -202,8 +202,13 @@ class _TableDistFn(torch.autograd.Function):
         b, n = vvd.shape
         dev = vvd.device
         if b == 0:
-            return (torch.zeros(ctx.tshape, dtype=torch.float64, device=dev), None,
-                    (None if wsum_w is None else torch.zeros_like(wsum_w)), None, None)
+            gt = torch.zeros(ctx.tshape, dtype=torch.float64, device=dev)
+            gw = None if wsum_w is None else torch.zeros_like(wsum_w)
+            if ctx.sync_grad:       # the other ranks are in the collective: take part
+                _allreduce_avg(gt)
+                if gw is not None:
+                    _allreduce_avg(gw)
+            return gt, None, gw, None, None, None
         with torch.cuda.device(dev):
             gt = torch.empty(ctx.tshape, dtype=torch.float64, device=dev)     # written, not accumulated (overwrite=1)
             gw = None
@@ -212,13 +217,26 @@ class _TableDistFn(torch.autograd.Function):
                 gw = torch.zeros(n, dtype=torch.float64, device=dev)
                 w_flat = wsum_w.contiguous().reshape(-1)
             ws, ws_bytes = backward_workspace_for(ctx.kind, n, ctx.tshape[0], dev)
-            _lib.check(lib.sympa_dist_backward_table(
-                _lib.KIND[ctx.kind], n, _lib.METRIC[ctx.metric], b, _ptr(grad_dist), _ptr(saved),
-                _ptr(gt), ctx.tshape[0], _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat), _ptr(gw),
-                _ptr(ws), ws_bytes, 1, _stream()))
+            k, m, rows = _lib.KIND[ctx.kind], _lib.METRIC[ctx.metric], ctx.tshape[0]
+            if ctx.sync_grad and ws is not None:
+                # data-parallel backward: scatter into the packed gradient table, all-reduce (average) THAT - the
+                # one collective of the path, on 62 % of the dense bytes at n = 4 - then write the dense rows
+                need = lib.sympa_backward_workspace_bytes(k, n, rows)
+                _lib.check(lib.sympa_table_grad_scatter(k, n, m, b, _ptr(grad_dist), _ptr(saved), rows, _ptr(idx.contiguous()),
+                                                        _ptr(vvd), _ptr(w_flat), _ptr(gw), _ptr(ws), ws_bytes, _stream()))
+                _allreduce_avg(ws[: need // 8])
+                _lib.check(lib.sympa_table_grad_expand(k, n, rows, _ptr(ws), _ptr(gt), 1, _stream()))
+            else:
+                _lib.check(lib.sympa_dist_backward_table(
+                    k, n, m, b, _ptr(grad_dist), _ptr(saved), _ptr(gt), rows, _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat),
+                    _ptr(gw), _ptr(ws), ws_bytes, 1, _stream()))
+                if ctx.sync_grad:
+                    _allreduce_avg(gt)
+            if ctx.sync_grad and gw is not None:
+                _allreduce_avg(gw)
         if gw is not None:
             gw = gw.reshape(wsum_w.shape)
-        return gt, None, gw, None, None
+        return gt, None, gw, None, None, None
 
 
 def dist(kind, metric, z1, z2, wsum_w=None):
@@ -226,8 +244,22 @@ def dist(kind, metric, z1, z2, wsum_w=None):
     return _DistFn.apply(z1, z2, wsum_w, kind, metric)
 
 
-def table_dist(kind, metric, table, idx, wsum_w=None):
-    return _TableDistFn.apply(table, idx, wsum_w, kind, metric)
+def _allreduce_avg(t):
+    """average over the ranks (what DDP does with the table gradient, train.py:59); no-op in a single process"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(dist.get_world_size())
+
+
+def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False):
+    """sync_grad=True: the backward also averages the table gradient (and dL/dw of wsum) over the ranks of
+    the default process group - on the packed gradient table where there is one - so the caller must NOT
+    all-reduce table.grad again."""
+    return _TableDistFn.apply(table, idx, wsum_w, kind, metric, bool(sync_grad))
 
 
 def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsum_w=None, grad_wsum_w=None,

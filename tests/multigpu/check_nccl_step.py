@@ -3,7 +3,8 @@
 (not collected by pytest: the -m gpu suite runs on one GPU; the same logic is covered on CPU with gloo in
 tests/test_distributed_gloo.py).  Checks, on every rank:
   * pairs sharded over the ranks + the averaged NCCL all-reduce of the table gradient == the full-batch
-    gradient of one GPU / world;
+    gradient of one GPU / world; the all-reduce issued inside the backward on the packed gradient table
+    (dist_from_table(..., sync_grad=True)) gives the same gradient;
   * the owner-computes optimizer step (reduce-scatter, fused sympa_rsgd_step on the owned rows,
     all-gather) leaves every rank with the table of the replicated step."""
 import os
@@ -46,6 +47,12 @@ def main():
     all_sel = torch.cat([sd.shard_indices(pairs, k, world, shuffle=True, seed=0, drop_last=True) for k in range(world)]).to(dev)
     full = grad_of(all_sel)
     torch.testing.assert_close(avg * world, full, rtol=1e-9, atol=1e-9 * full.abs().max().item())
+
+    # the same all-reduce issued inside the backward, on the packed gradient table (sync_grad=True)
+    t = table.clone().requires_grad_(True)
+    d = man.dist_from_table(t, idx[shard].contiguous(), sync_grad=True)
+    (torch.abs((d / gd[shard]) ** 2 - 1)).sum().backward()
+    torch.testing.assert_close(t.grad, avg, rtol=1e-10, atol=1e-12 * full.abs().max().item())
 
     lr = 0.05
     rep = table.clone()

@@ -534,3 +534,31 @@ def test_fused_epoch_runner_equals_train_epoch(sb, manifold, metric, n, use_grap
         torch.testing.assert_close(model.manifold.metric.weights.detach(), ref.manifold.metric.weights.detach(),
                                    rtol=1e-7, atol=1e-10)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 4), ("bounded", 3), ("upper", 8)])
+def test_sync_grad_backward_route_equals_plain_backward_on_one_rank(sb, kind, n):
+    """dist_from_table(..., sync_grad=True): scatter into the packed gradient table / [all-reduce] / expansion as
+    separate ABI calls.  In a single process the collective is a no-op and the gradient must equal the plain
+    backward's (the multi-rank behaviour is checked by tests/multigpu/check_nccl_step.py under torchrun)."""
+    rows, pairs = 50, 300
+    g = torch.Generator().manual_seed(9)
+    table = so.upper_spread(rows, n, generator=g, scale=0.3)
+    if kind == "bounded":
+        table = so.to_symmetric(so.cayley_transform(table))
+    src = torch.randint(0, rows, (pairs,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (pairs,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    go = torch.randn(pairs, generator=g, dtype=torch.float64).cuda()
+    man = make_manifold(sb, kind, n, "wsum", np.linspace(0.3, 1.2, n))
+    grads = {}
+    for sync in (False, True):
+        t = table.clone().cuda().requires_grad_(True)
+        man.metric.weights.grad = None
+        d = man.dist_from_table(t, idx, sync_grad=sync)
+        (d * go).sum().backward()
+        grads[sync] = (t.grad.clone(), man.metric.weights.grad.clone())
+    tol = 1e-12 * grads[False][0].abs().max().item()
+    torch.testing.assert_close(grads[True][0], grads[False][0], rtol=1e-12, atol=tol)
+    torch.testing.assert_close(grads[True][1], grads[False][1], rtol=1e-12, atol=1e-12)
+    sb.ops.check_status()
