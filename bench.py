@@ -187,7 +187,7 @@ def run_ours(args):
         return loss
 
     # host-resident inputs for the e2e leg
-    idx_h = idx.cpu().pin_memory()
+    idx_h = idx.to(torch.int32).cpu().pin_memory()    # node ids as int32 on the host, widened on the device by the feeder
     gd_h = gd.cpu().pin_memory()
     loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
 
@@ -353,10 +353,10 @@ def run_ours(args):
                    "l2": "table + saved unit gradients + indices exceed L2 every step (no explicit flush needed)",
                    "parallelism": f"dp{world} pairs sharded, table replicated, one NCCL all-reduce (average) of the packed "
                                   "table gradient inside the backward"},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(idx_h.numel() * 8 + gd_h.numel() * 8),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(idx_h.numel() * idx_h.element_size() + gd_h.numel() * gd_h.element_size()),
                 "d2h_bytes_per_step": 8,
-                "how": "manifold.dist_from_table + AverageDistortionLoss + backward per step; every step's index pairs and "
-                       "graph distances are copied from pinned host memory (sympa_b200.feeder.PairFeeder: the copy of step "
+                "how": "manifold.dist_from_table + AverageDistortionLoss + backward per step; every step's index pairs (int32 "
+                       "on the host, widened on the device) and graph distances (float64) are copied from pinned host memory (sympa_b200.feeder.PairFeeder: the copy of step "
                        "k+1 overlaps the compute of step k on a side stream; the first copy is exposed), the loss is read "
                        "back and the host waits for it every step"},
         # our kernels per step: forward+unit-gradient kernel, then either the direct scatter (1) or the packed scatter +

@@ -4,7 +4,8 @@ The reference keeps all triplets on the device (train.py:95-96); for graphs whos
 not fit (5e11 pairs, sampled) or that arrive from a host-side sampler, the
 batch (index pairs int64 (b, 2), graph distances float64 (b,)) has to cross PCIe every step.
 PairFeeder double-buffers that copy on a side stream: while batch k computes, batch k + 1 is on the
-wire, so a step costs max(copy, compute) instead of their sum.  Host tensors must be pinned.
+wire, so a step costs max(copy, compute) instead of their sum.  Host tensors must be pinned.  The index
+pairs may be int32 on the host (node ids fit; half the bytes): they are widened to int64 on the device.
 """
 import torch
 
@@ -27,14 +28,20 @@ class PairFeeder:
         assert idx_h.is_pinned() and gd_h.is_pinned(), "PairFeeder needs pinned host memory"
         s = self._head
         buf = self._bufs[s]
-        if buf is None or buf[0].shape != idx_h.shape or buf[1].shape != gd_h.shape:
-            buf = (torch.empty(idx_h.shape, dtype=idx_h.dtype, device=self.device),
-                   torch.empty(gd_h.shape, dtype=gd_h.dtype, device=self.device))
+        narrow = idx_h.dtype == torch.int32     # node ids as int32 on the host: 8 instead of 16 bytes per pair on the wire
+        if buf is None or buf[0].shape != idx_h.shape or buf[1].shape != gd_h.shape or (buf[2] is None) == narrow:
+            buf = (torch.empty(idx_h.shape, dtype=torch.int64, device=self.device),
+                   torch.empty(gd_h.shape, dtype=gd_h.dtype, device=self.device),
+                   torch.empty(idx_h.shape, dtype=torch.int32, device=self.device) if narrow else None)
             self._bufs[s] = buf
         with torch.cuda.stream(self.copy_stream):
             if self._consumed[s] is not None:
                 self.copy_stream.wait_event(self._consumed[s])   # the step that read this slot is done with it
-            buf[0].copy_(idx_h, non_blocking=True)
+            if narrow:
+                buf[2].copy_(idx_h, non_blocking=True)
+                buf[0].copy_(buf[2])                             # widened on the device (the kernels take int64 indices)
+            else:
+                buf[0].copy_(idx_h, non_blocking=True)
             buf[1].copy_(gd_h, non_blocking=True)
             self._ready[s].record(self.copy_stream)
         self._head = (s + 1) % self.depth
@@ -46,7 +53,7 @@ class PairFeeder:
         s = self._tail
         torch.cuda.current_stream(self.device).wait_event(self._ready[s])
         self._cur = s
-        return self._bufs[s]
+        return self._bufs[s][0], self._bufs[s][1]
 
     def done(self):
         """Call after the last kernel that reads the batch handed out by next() has been enqueued."""

@@ -562,3 +562,25 @@ def test_sync_grad_backward_route_equals_plain_backward_on_one_rank(sb, kind, n)
     torch.testing.assert_close(grads[True][0], grads[False][0], rtol=1e-12, atol=tol)
     torch.testing.assert_close(grads[True][1], grads[False][1], rtol=1e-12, atol=1e-12)
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_pair_feeder_double_buffering_delivers_batches_in_order(sb, idx_dtype):
+    """PairFeeder: batches submitted from pinned host memory come out in order, as int64 indices and float64
+    distances on the device, while later batches are already on the wire (slots are reused only after done())."""
+    from sympa_b200.feeder import PairFeeder
+    feeder = PairFeeder(torch.device("cuda", torch.cuda.current_device()))
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randint(0, 1000, (257, 2), generator=g).to(idx_dtype).pin_memory(),
+                torch.rand(257, generator=g, dtype=torch.float64).pin_memory()) for _ in range(5)]
+    feeder.submit(*batches[0])
+    for k in range(5):
+        idx_d, gd_d = feeder.next()
+        if k + 1 < 5:
+            feeder.submit(*batches[k + 1])
+        assert idx_d.dtype == torch.int64 and idx_d.is_cuda and gd_d.dtype == torch.float64
+        got_idx, got_gd = idx_d.clone(), gd_d.clone()     # "compute" on the current stream
+        feeder.done()
+        assert torch.equal(got_idx.cpu(), batches[k][0].to(torch.int64)) and torch.equal(got_gd.cpu(), batches[k][1])
+    with pytest.raises(AssertionError):
+        feeder.next()                                     # nothing left in flight
