@@ -155,7 +155,12 @@ def make_pairs(rows, b, device, seed):
     return torch.stack((src, dst), 1).contiguous(), gd
 
 
-def distortion_loss(graph_dist, manifold_dist):   # sympa/losses.py:16-19, torch ops on (b,) vectors
+def distortion_loss(graph_dist, manifold_dist):
+    """sympa/losses.py:16-19.  GPU legs: the package's AverageDistortionLoss (same expression, one kernel forward
+    and one backward on CUDA float64 vectors); CPU legs (baseline / reference arm): the reference's torch ops."""
+    if manifold_dist.is_cuda:
+        from sympa_b200.losses import AverageDistortionLoss
+        return AverageDistortionLoss().calculate_loss(graph_dist, manifold_dist)
     return torch.abs(torch.pow(manifold_dist / graph_dist, 2) - 1).sum()
 
 

@@ -164,6 +164,15 @@ int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs,
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table,
                             int overwrite, void* stream);
 
+/* AverageDistortionLoss.calculate_loss (sympa/losses.py:10-19): loss_out (1 double, ACCUMULATED into) +=
+ * sum_p |(manifold_dist_p / graph_dist_p)^2 - 1|, and its backward grad_manifold_dist_p = grad_loss *
+ * sign(.) * 2 manifold_dist_p / graph_dist_p^2 (grad_loss: 1 device double) - one kernel each instead of the
+ * ~11 element-wise torch kernels of the Python expression (5 % of a step at n = 4). */
+int sympa_distortion_loss_forward(int64_t num_pairs, const double* graph_dist, const double* manifold_dist,
+                                  double* loss_out, void* stream);
+int sympa_distortion_loss_backward(int64_t num_pairs, const double* graph_dist, const double* manifold_dist,
+                                   const double* grad_loss, double* grad_manifold_dist, void* stream);
+
 /* One fused launch for a training step of the distortion objective (sympa/losses.py:16-19 with
  * the scale of sympa/model.py:30):   L = sum_p | (scale * dist_p / graph_dist_p)^2 - 1 |.
  * Gathers both rows, computes dist, the loss term and its derivative, and scatter-adds

@@ -37,6 +37,8 @@ EXPORTS = (
     "sympa_dist_backward_table",
     "sympa_table_grad_scatter",
     "sympa_table_grad_expand",
+    "sympa_distortion_loss_forward",
+    "sympa_distortion_loss_backward",
 )
 
 _lib = None
@@ -88,6 +90,10 @@ def load():
     lib.sympa_table_grad_scatter.argtypes = [I, I, I, L, P, P, L, P, P, P, P, P, L, P]
     lib.sympa_table_grad_expand.restype = I
     lib.sympa_table_grad_expand.argtypes = [I, I, L, P, P, I, P]
+    lib.sympa_distortion_loss_forward.restype = I
+    lib.sympa_distortion_loss_forward.argtypes = [L, P, P, P, P]
+    lib.sympa_distortion_loss_backward.restype = I
+    lib.sympa_distortion_loss_backward.argtypes = [L, P, P, P, P, P]
     _lib = lib
     return lib
 

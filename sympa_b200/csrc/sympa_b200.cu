@@ -207,6 +207,42 @@ __global__ void __launch_bounds__(256) zero_diagonal_kernel(int64_t row_begin, i
   if (r < row_count && row_begin + r < num_rows) out[r * num_rows + row_begin + r] = 0.0;
 }
 
+// AverageDistortionLoss (sympa/losses.py:10-19): L = sum_p | (d_p / g_p)^2 - 1 |, as one kernel forward and one
+// backward instead of the five + six element-wise torch kernels of the Python expression.
+__global__ void __launch_bounds__(256) distortion_loss_fwd_kernel(int64_t b, const double* __restrict__ g,
+                                                                  const double* __restrict__ d, double* __restrict__ loss) {
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < b; p += stride) {
+    const double r = __ldg(d + p) / __ldg(g + p);
+    acc += fabs(r * r - 1.0);
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    atomicAdd(loss, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) distortion_loss_bwd_kernel(int64_t b, const double* __restrict__ g,
+                                                                  const double* __restrict__ d,
+                                                                  const double* __restrict__ grad_loss,
+                                                                  double* __restrict__ grad_d) {
+  const double go = __ldg(grad_loss);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < b; p += stride) {
+    const double gi = 1.0 / __ldg(g + p);
+    const double r = __ldg(d + p) * gi;
+    const double e = r * r - 1.0;
+    const double sg = e > 0.0 ? 1.0 : (e < 0.0 ? -1.0 : 0.0);   // torch.abs backward: sign, 0 at 0
+    grad_d[p] = go * sg * 2.0 * r * gi;
+  }
+}
+
 // FP64 FMA throughput probe (diagnostic: gives bench.py a MEASURED FP64 roofline denominator; the
 // driver's MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).  8 independent FMA chains/thread.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed, double* __restrict__ out) {
@@ -503,6 +539,27 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const do
     rc = check_launch();
   }
   return rc;
+}
+
+int sympa_distortion_loss_forward(int64_t num_pairs, const double* graph_dist, const double* manifold_dist,
+                                  double* loss_out, void* stream) {
+  if (num_pairs < 0 || loss_out == nullptr) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  if (graph_dist == nullptr || manifold_dist == nullptr) return SYMPA_ERR_BAD_ARG;
+  distortion_loss_fwd_kernel<<<grid_for(num_pairs, 256, 8), 256, 0, (cudaStream_t)stream>>>(num_pairs, graph_dist,
+                                                                                          manifold_dist, loss_out);
+  return check_launch();
+}
+
+int sympa_distortion_loss_backward(int64_t num_pairs, const double* graph_dist, const double* manifold_dist,
+                                   const double* grad_loss, double* grad_manifold_dist, void* stream) {
+  if (num_pairs < 0) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  if (graph_dist == nullptr || manifold_dist == nullptr || grad_loss == nullptr || grad_manifold_dist == nullptr)
+    return SYMPA_ERR_BAD_ARG;
+  distortion_loss_bwd_kernel<<<grid_for(num_pairs, 256, 32), 256, 0, (cudaStream_t)stream>>>(
+      num_pairs, graph_dist, manifold_dist, grad_loss, grad_manifold_dist);
+  return check_launch();
 }
 
 int64_t sympa_backward_workspace_bytes(int kind, int n, int64_t num_rows) {

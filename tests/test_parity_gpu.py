@@ -584,3 +584,27 @@ def test_pair_feeder_double_buffering_delivers_batches_in_order(sb, idx_dtype):
         assert torch.equal(got_idx.cpu(), batches[k][0].to(torch.int64)) and torch.equal(got_gd.cpu(), batches[k][1])
     with pytest.raises(AssertionError):
         feeder.next()                                     # nothing left in flight
+
+
+@pytest.mark.parametrize("shape", [(1000,), (257, 1), (0,)])
+def test_fused_distortion_loss_equals_reference_expression(sb, shape):
+    """sympa_b200.losses.AverageDistortionLoss on CUDA vectors (one kernel each way) against the reference's torch
+    expression (sympa/losses.py:16-19), values and gradient, including the sign(0) = 0 convention of torch.abs."""
+    from sympa_b200.losses import AverageDistortionLoss
+    g = torch.Generator().manual_seed(4)
+    gd = torch.randint(1, 20, shape, generator=g).double().cuda()
+    d0 = (gd * (0.5 + torch.rand(shape, generator=g, dtype=torch.float64).cuda()))
+    if d0.numel() > 3:
+        d0.view(-1)[3] = gd.view(-1)[3]               # (d / g)^2 - 1 == 0 exactly: gradient 0
+    outs = []
+    for fused in (True, False):
+        d = d0.clone().requires_grad_(True)
+        if fused:
+            loss = AverageDistortionLoss().calculate_loss(gd, d)
+        else:
+            loss = torch.abs(torch.pow(d / gd, 2) - 1).sum()
+        (3.0 * loss).backward()
+        outs.append((loss.detach(), d.grad.clone()))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-12, atol=1e-14)
+    assert outs[0][1].shape == d0.shape
