@@ -27,7 +27,11 @@
 extern "C" {
 #endif
 
-#define SYMPA_ABI_VERSION 2
+/* 3: v2 plus additive entry points (sympa_dist_matrix, sympa_dist_backward_table, sympa_table_grad_scatter /
+ *    _expand, sympa_rsgd_step_ex, sympa_distortion_loss_forward / _backward) and the bounded domain in
+ *    sympa_rsgd_step; the saved state of the register-kernel sizes became packed (its size still comes from
+ *    sympa_workspace_bytes, its layout was never part of the interface). */
+#define SYMPA_ABI_VERSION 3
 
 /* manifold kinds: sympa/embeddings.py:144-149 ("upper", "bounded") and :142 ("spd") */
 enum { SYMPA_KIND_UPPER = 0, SYMPA_KIND_BOUNDED = 1, SYMPA_KIND_SPD = 2 };

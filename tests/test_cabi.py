@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.sympa_version() == 2
+    assert lib.sympa_version() == 3
     assert lib.sympa_error_string(0) == b"ok"
     assert lib.sympa_error_string(2).startswith(b"unsupported")
     # 2 operands * pairs * (2 n n) doubles * 8 bytes
