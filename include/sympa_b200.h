@@ -168,6 +168,20 @@ int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs,
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table,
                             int overwrite, void* stream);
 
+/* Bounded domain by rows.  BoundedDomainManifold.dist (bounded_domain.py:27-39) maps both operands to the upper
+ * half space with the inverse Cayley transform and calls the upper-half dist.  The transform acts on points,
+ * so on the table path it can be applied ONCE PER TABLE ROW instead of once per pair and operand:
+ *   sympa_bounded_rows_to_upper   upper_out[r] = i (I + z_r)(I - z_r)^-1      (num_rows, 2, n, n)
+ *   ... sympa_dist_forward / backward with SYMPA_KIND_UPPER on upper_out ...
+ *   sympa_bounded_rows_backward   grad_table[r] (=, +=) conj(N_r) (2 G_Y - 2i G_X) conj(N_r),  N_r = (I - z_r)^-1,
+ *                                 G = grad_upper[r] the (symmetric) upper-half gradient of the row
+ * Worth it when the batch covers the table densely; the per-pair bounded kernels remain for materialised
+ * operands and sparse batches. */
+int sympa_bounded_rows_to_upper(int n, int64_t num_rows, const double* table, double* upper_out,
+                                unsigned int* status, void* stream);
+int sympa_bounded_rows_backward(int n, int64_t num_rows, const double* table, const double* grad_upper,
+                                double* grad_table, int overwrite, void* stream);
+
 /* AverageDistortionLoss.calculate_loss (sympa/losses.py:10-19): loss_out (1 double, ACCUMULATED into) +=
  * sum_p |(manifold_dist_p / graph_dist_p)^2 - 1|, and its backward grad_manifold_dist_p = grad_loss *
  * sign(.) * 2 manifold_dist_p / graph_dist_p^2 (grad_loss: 1 device double) - one kernel each instead of the

@@ -39,6 +39,8 @@ EXPORTS = (
     "sympa_table_grad_expand",
     "sympa_distortion_loss_forward",
     "sympa_distortion_loss_backward",
+    "sympa_bounded_rows_to_upper",
+    "sympa_bounded_rows_backward",
 )
 
 _lib = None
@@ -94,6 +96,10 @@ def load():
     lib.sympa_distortion_loss_forward.argtypes = [L, P, P, P, P]
     lib.sympa_distortion_loss_backward.restype = I
     lib.sympa_distortion_loss_backward.argtypes = [L, P, P, P, P, P]
+    lib.sympa_bounded_rows_to_upper.restype = I
+    lib.sympa_bounded_rows_to_upper.argtypes = [I, L, P, P, P, P]
+    lib.sympa_bounded_rows_backward.restype = I
+    lib.sympa_bounded_rows_backward.argtypes = [I, L, P, P, P, I, P]
     _lib = lib
     return lib
 

@@ -76,6 +76,22 @@ struct RsgdArgs {
 template <int N>
 int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t stream);
 
+// Bounded domain by rows (the inverse Cayley transform acts on POINTS, not on pairs): forward maps every
+// table row z -> Z = i (I + z)(I - z)^-1 once, so that the pairs can run the cheaper upper-half kernels on
+// the transformed table; backward maps the accumulated upper-half gradient of a row back through the
+// transform, G_z = conj(Nz) (2 G_Y - 2i G_X) conj(Nz), Nz = (I - z)^-1  (bounded_domain.py:27-39).
+struct BoundedRowsArgs {
+  int64_t num_rows;
+  const double* table;      // (num_rows, 2, n, n) bounded points
+  double* upper_out;        // forward: transformed points
+  const double* grad_upper; // backward: dL/dZ rows (symmetric blocks)
+  double* grad_table;       // backward: dL/dz rows
+  int overwrite;            // backward: write (1) or accumulate (0)
+  unsigned int* status;
+};
+template <int N>
+int launch_bounded_rows(int backward, const BoundedRowsArgs& a, cudaStream_t stream);
+
 int check_launch();
 int grid_for(int64_t work_items, int threads, int waves_cap);
 
@@ -742,6 +758,61 @@ int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t s) {
     rsgd_kernel<N, kBounded><<<grid, kThreads, 0, s>>>(a);
   else
     return 2;
+  return check_launch();
+}
+
+template <int N, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads) bounded_rows_kernel(const BoundedRowsArgs a) {
+  constexpr bool REG = N <= SY_REG_MAX_N;
+  constexpr int T = Cfg<N>::kTri;
+  constexpr int PER = 2 * N * N;
+  unsigned st = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.num_rows; r += stride) {
+    double zr[T], zi[T], x[T], y[T], u[T], v[T];
+    load_packed<N, REG>(a.table + r * PER, zr);
+    load_packed<N, REG>(a.table + r * PER + N * N, zi);
+    const bool ok = REG ? reg::bounded_to_upper<N>(zr, zi, x, y, u, v) : loc::bounded_to_upper<N>(zr, zi, x, y, u, v);
+    if (!BACKWARD) {
+      if (!ok) st |= kStatusNotPD;
+      store_full<N, REG>(a.upper_out + r * PER, x);
+      store_full<N, REG>(a.upper_out + r * PER + N * N, y);
+    } else {
+      double gx[T], gy[T], nr[T], ni[T], gr[T], gi[T];
+      load_packed<N, REG>(a.grad_upper + r * PER, gx);
+      load_packed<N, REG>(a.grad_upper + r * PER + N * N, gy);
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        nr[i] = 2.0 * gy[i];
+        ni[i] = -2.0 * gx[i];
+        v[i] = -v[i];
+      }
+      if (REG) reg::csym_sandwich<N>(u, v, nr, ni, 1.0, gr, gi); else loc::csym_sandwich<N>(u, v, nr, ni, 1.0, gr, gi);
+      double* o = a.grad_table + r * PER;
+      if (!a.overwrite) {
+        double pr[T], pi[T];
+        load_packed<N, REG>(o, pr);
+        load_packed<N, REG>(o + N * N, pi);
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+          gr[i] += pr[i];
+          gi[i] += pi[i];
+        }
+      }
+      store_full<N, REG>(o, gr);
+      store_full<N, REG>(o + N * N, gi);
+    }
+  }
+  if (!BACKWARD && st != 0 && a.status != nullptr) atomicOr(a.status, st);
+}
+
+template <int N>
+int launch_bounded_rows(int backward, const BoundedRowsArgs& a, cudaStream_t s) {
+  const int grid = grid_for(a.num_rows, kThreads, 16);
+  if (backward)
+    bounded_rows_kernel<N, true><<<grid, kThreads, 0, s>>>(a);
+  else
+    bounded_rows_kernel<N, false><<<grid, kThreads, 0, s>>>(a);
   return check_launch();
 }
 

@@ -9,4 +9,5 @@
 namespace sympa {
 template int launch_pairs<SYMPA_TU_N>(int, int, const PairArgs&, cudaStream_t);
 template int launch_rsgd<SYMPA_TU_N>(int, const RsgdArgs&, cudaStream_t);
+template int launch_bounded_rows<SYMPA_TU_N>(int, const BoundedRowsArgs&, cudaStream_t);
 }

@@ -298,7 +298,8 @@ int grid_for(int64_t work_items, int threads, int waves_cap) {
 
 #define SY_DECL(K)                                                                  \
   extern template int launch_pairs<K>(int, int, const PairArgs&, cudaStream_t);     \
-  extern template int launch_rsgd<K>(int, const RsgdArgs&, cudaStream_t);
+  extern template int launch_rsgd<K>(int, const RsgdArgs&, cudaStream_t);     \
+  extern template int launch_bounded_rows<K>(int, const BoundedRowsArgs&, cudaStream_t);
 SY_DECL(1) SY_DECL(2) SY_DECL(3) SY_DECL(4) SY_DECL(5) SY_DECL(6) SY_DECL(7) SY_DECL(8) SY_DECL(9) SY_DECL(10)
 #undef SY_DECL
 
@@ -307,6 +308,17 @@ static int launch_n(int n, int kind, int mode, const PairArgs& a, cudaStream_t s
 #define SY_CASE(K) \
   case K:          \
     return launch_pairs<K>(kind, mode, a, s);
+    SY_CASE(1) SY_CASE(2) SY_CASE(3) SY_CASE(4) SY_CASE(5) SY_CASE(6) SY_CASE(7) SY_CASE(8) SY_CASE(9) SY_CASE(10)
+#undef SY_CASE
+  }
+  return SYMPA_ERR_UNSUPPORTED;
+}
+
+static int launch_bounded_rows_n(int n, int backward, const BoundedRowsArgs& a, cudaStream_t s) {
+  switch (n) {
+#define SY_CASE(K) \
+  case K:          \
+    return launch_bounded_rows<K>(backward, a, s);
     SY_CASE(1) SY_CASE(2) SY_CASE(3) SY_CASE(4) SY_CASE(5) SY_CASE(6) SY_CASE(7) SY_CASE(8) SY_CASE(9) SY_CASE(10)
 #undef SY_CASE
   }
@@ -539,6 +551,34 @@ int sympa_dist_backward(int kind, int n, int metric, int64_t num_pairs, const do
     rc = check_launch();
   }
   return rc;
+}
+
+int sympa_bounded_rows_to_upper(int n, int64_t num_rows, const double* table, double* upper_out, unsigned int* status,
+                                void* stream) {
+  if (n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
+  if (num_rows < 0 || (num_rows > 0 && (table == nullptr || upper_out == nullptr))) return SYMPA_ERR_BAD_ARG;
+  if (num_rows == 0) return SYMPA_OK;
+  BoundedRowsArgs a = {};
+  a.num_rows = num_rows;
+  a.table = table;
+  a.upper_out = upper_out;
+  a.status = status;
+  return launch_bounded_rows_n(n, 0, a, (cudaStream_t)stream);
+}
+
+int sympa_bounded_rows_backward(int n, int64_t num_rows, const double* table, const double* grad_upper,
+                                double* grad_table, int overwrite, void* stream) {
+  if (n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
+  if (num_rows < 0 || (num_rows > 0 && (table == nullptr || grad_upper == nullptr || grad_table == nullptr)))
+    return SYMPA_ERR_BAD_ARG;
+  if (num_rows == 0) return SYMPA_OK;
+  BoundedRowsArgs a = {};
+  a.num_rows = num_rows;
+  a.table = table;
+  a.grad_upper = grad_upper;
+  a.grad_table = grad_table;
+  a.overwrite = overwrite;
+  return launch_bounded_rows_n(n, 1, a, (cudaStream_t)stream);
 }
 
 int sympa_distortion_loss_forward(int64_t num_pairs, const double* graph_dist, const double* manifold_dist,

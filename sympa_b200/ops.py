@@ -7,6 +7,10 @@ import torch
 
 from . import _lib
 
+# bounded domain on the table path: transform the rows once instead of both operands of every pair when the
+# batch covers the table densely (set to False to force the per-pair bounded kernels)
+BOUNDED_BY_ROWS = True
+
 _status_words = {}
 _scratch = {}
 
@@ -188,15 +192,30 @@ class _TableDistFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
-        dist, vvd, saved = forward_raw(kind, metric, table=table, idx=idx, wsum_w=wsum_w, want_grad=need)
-        ctx.kind, ctx.metric, ctx.tshape, ctx.sync_grad = kind, metric, table.shape, sync_grad
-        ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None)
+        # bounded domain, batch covering the table densely: the inverse Cayley transform is applied once per
+        # table row (sympa_bounded_rows_to_upper) and the pairs run the upper-half kernels on the result
+        # (break-even in flops is 2 pairs per row.  Only for n <= 6, where the row kernels are the unrolled register
+        # code: the rolled local-memory row kernels of the larger sizes measured far slower than they save -
+        # bounded n = 10 18.9 -> 8.2 M pairs/s on a 2^20-row table)
+        by_rows = (kind == "bounded" and BOUNDED_BY_ROWS and table.is_cuda and idx.dim() == 2 and table.shape[-1] <= 6
+                   and 2 * idx.shape[0] >= table.shape[0] > 0)
+        src = table
+        if by_rows:
+            t = _require(table, "table").detach()
+            src = torch.empty_like(t)
+            with torch.cuda.device(t.device):
+                _lib.check(_lib.load().sympa_bounded_rows_to_upper(t.shape[-1], t.shape[0], _ptr(t), _ptr(src),
+                                                                   _ptr(status_word(t.device)), _stream()))
+        kk = "upper" if by_rows else kind
+        dist, vvd, saved = forward_raw(kk, metric, table=src, idx=idx, wsum_w=wsum_w, want_grad=need)
+        ctx.kind, ctx.metric, ctx.tshape, ctx.sync_grad, ctx.by_rows = kk, metric, table.shape, sync_grad, by_rows
+        ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None, table.detach() if by_rows else None)
         ctx.mark_non_differentiable(vvd)
         return dist, vvd
 
     @staticmethod
     def backward(ctx, grad_dist, _grad_vvd):
-        saved, vvd, idx, wsum_w = ctx.saved_tensors
+        saved, vvd, idx, wsum_w, ztable = ctx.saved_tensors
         lib = _lib.load()
         grad_dist = _require(grad_dist, "grad_dist")
         b, n = vvd.shape
@@ -234,6 +253,10 @@ class _TableDistFn(torch.autograd.Function):
                     _allreduce_avg(gt)
             if ctx.sync_grad and gw is not None:
                 _allreduce_avg(gw)
+            if ctx.by_rows:   # gt is the gradient with respect to the transformed rows: back through the transform
+                gz = torch.empty_like(gt)
+                _lib.check(lib.sympa_bounded_rows_backward(n, rows, _ptr(ztable), _ptr(gt), _ptr(gz), 1, _stream()))
+                gt = gz
         if gw is not None:
             gw = gw.reshape(wsum_w.shape)
         return gt, None, gw, None, None, None

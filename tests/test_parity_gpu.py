@@ -205,7 +205,9 @@ def test_full_size_properties(sb, kind, n):
     assert bool((v[:, 1:] >= v[:, :-1]).all())
     torch.testing.assert_close(out["riem"], v.norm(dim=-1), rtol=1e-12, atol=0)
     torch.testing.assert_close(out["fone"], v.sum(-1), rtol=1e-12, atol=0)
-    torch.testing.assert_close(out["finf"], v[:, -1], rtol=0, atol=0)
+    # (dist on the table path and vvd on materialised operands may run different kernel instantiations - for the
+    # bounded domain the by-rows route against the per-pair kernel - so equal up to FMA contraction, not bitwise)
+    torch.testing.assert_close(out["finf"], v[:, -1], rtol=1e-12, atol=0)
     same = torch.stack((idx[:, 0], idx[:, 0]), 1)
     with torch.no_grad():
         dxx = man.dist_from_table(table, same)
@@ -608,3 +610,68 @@ def test_fused_distortion_loss_equals_reference_expression(sb, shape):
     torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-12, atol=1e-14)
     assert outs[0][1].shape == d0.shape
+
+
+@pytest.mark.parametrize("n,metric", [(2, "finf"), (3, "fone"), (4, "riem"), (5, "fmin"), (6, "wsum")])
+def test_bounded_by_rows_equals_per_pair_bounded_kernels_and_oracle(sb, n, metric):
+    """Bounded domain on the table path with a dense batch: inverse Cayley transform once per table row
+    (sympa_bounded_rows_to_upper), upper-half kernels on the pairs, gradient mapped back per row
+    (sympa_bounded_rows_backward) - against the per-pair bounded kernels and the oracle (bounded_domain.py:27-39)."""
+    rows, pairs = 40, 200
+    g = torch.Generator().manual_seed(21 + n)
+    table = so.to_symmetric(so.cayley_transform(so.upper_spread(rows, n, generator=g, scale=0.3)))
+    src = torch.randint(0, rows, (pairs,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (pairs,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1)
+    go = torch.rand(pairs, generator=g, dtype=torch.float64) + 0.5
+    w = np.linspace(0.3, 1.2, n) if metric == "wsum" else None
+    man = make_manifold(sb, "bounded", n, metric, w)
+    res = {}
+    for by_rows in (True, False):
+        sb.ops.BOUNDED_BY_ROWS = by_rows
+        try:
+            t = table.clone().cuda().requires_grad_(True)
+            if metric == "wsum":
+                man.metric.weights.grad = None
+            d = man.dist_from_table(t, idx.cuda())
+            (d * go.cuda()).sum().backward()
+            res[by_rows] = (d.detach().cpu(), t.grad.cpu(), None if metric != "wsum" else man.metric.weights.grad.cpu().clone())
+        finally:
+            sb.ops.BOUNDED_BY_ROWS = True
+    gmax = res[False][1].abs().max().item()
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-11, atol=1e-13)
+    assert (res[True][1] - res[False][1]).abs().max().item() <= 1e-9 * gmax
+    if metric == "wsum":
+        torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-9, atol=1e-12)
+    to = table.clone().requires_grad_(True)
+    do = so.dist("bounded", to[idx[:, 0]], to[idx[:, 1]], metric, None if w is None else torch.tensor(w))
+    (do * go).sum().backward()
+    torch.testing.assert_close(res[True][0], do.detach(), rtol=RTOL, atol=ATOL)
+    assert (res[True][1] - so.sym(to.grad)).abs().max().item() <= grad_tolerance(n) * gmax
+    sb.ops.check_status()
+
+
+@pytest.mark.parametrize("n", [7, 10])
+def test_bounded_row_kernels_large_n(sb, n):
+    """sympa_bounded_rows_to_upper / _backward for the sizes the dispatcher does not route through them (rolled row
+    kernels): still exact against the oracle's inverse Cayley transform and its autograd backward."""
+    from sympa_b200 import _lib
+    lib = _lib.load()
+    rows = 33
+    g = torch.Generator().manual_seed(n)
+    up = so.upper_spread(rows, n, generator=g, scale=0.3)
+    z = so.to_symmetric(so.cayley_transform(up))
+    zc = z.cuda()
+    out = torch.empty_like(zc)
+    st = sb.ops.status_word(zc.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.sympa_bounded_rows_to_upper(n, rows, zc.data_ptr(), out.data_ptr(), st.data_ptr(), stream))
+    torch.testing.assert_close(out.cpu(), up, rtol=1e-9, atol=1e-11)
+    gu = so.sym(torch.randn(rows, 2, n, n, generator=g, dtype=torch.float64))
+    zr = z.clone().requires_grad_(True)
+    (so.inverse_cayley_transform(zr) * gu).sum().backward()
+    gz = torch.full_like(zc, float("nan"))
+    _lib.check(lib.sympa_bounded_rows_backward(n, rows, zc.data_ptr(), gu.cuda().data_ptr(), gz.data_ptr(), 1, stream))
+    ref = so.sym(zr.grad)
+    assert (gz.cpu() - ref).abs().max().item() <= 1e-9 * ref.abs().max().item()
+    sb.ops.check_status()
