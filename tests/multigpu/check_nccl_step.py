@@ -54,6 +54,20 @@ def main():
     (torch.abs((d / gd[shard]) ** 2 - 1)).sum().backward()
     torch.testing.assert_close(t.grad, avg, rtol=1e-10, atol=1e-12 * full.abs().max().item())
 
+    # bounded domain, by-rows route (inverse Cayley per table row) with the in-backward all-reduce
+    from sympa_b200 import BoundedDomainManifold
+    btable = so.to_symmetric(so.cayley_transform(table.cpu())).to(dev)
+    bman = BoundedDomainManifold(dims=n, metric=MetricType.from_str("fone")).to(dev)
+    grads = []
+    for sync in (False, True):
+        t = btable.clone().requires_grad_(True)
+        d = bman.dist_from_table(t, idx[shard].contiguous(), sync_grad=sync)
+        (torch.abs((d / gd[shard]) ** 2 - 1)).sum().backward()
+        if not sync:
+            sd.allreduce_gradients([t.grad], average=True)
+        grads.append(t.grad.clone())
+    torch.testing.assert_close(grads[1], grads[0], rtol=1e-10, atol=1e-12 * grads[0].abs().max().item())
+
     lr = 0.05
     rep = table.clone()
     ops.rsgd_step("upper", rep, avg, lr)
