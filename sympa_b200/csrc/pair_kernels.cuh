@@ -763,7 +763,7 @@ int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t s) {
 
 template <int N, bool BACKWARD>
 __global__ void __launch_bounds__(kThreads) bounded_rows_kernel(const BoundedRowsArgs a) {
-  constexpr bool REG = N <= SY_REG_MAX_N;
+  constexpr bool REG = N <= reg_max_n(kBounded);
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = 2 * N * N;
   unsigned st = 0;

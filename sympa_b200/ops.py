@@ -194,10 +194,10 @@ class _TableDistFn(torch.autograd.Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         # bounded domain, batch covering the table densely: the inverse Cayley transform is applied once per
         # table row (sympa_bounded_rows_to_upper) and the pairs run the upper-half kernels on the result
-        # (break-even in flops is 2 pairs per row.  Only for n <= 6, where the row kernels are the unrolled register
+        # (break-even in flops is 2 pairs per row.  Only for n <= 7, where the row kernels are the unrolled register
         # code: the rolled local-memory row kernels of the larger sizes measured far slower than they save -
         # bounded n = 10 18.9 -> 8.2 M pairs/s on a 2^20-row table)
-        by_rows = (kind == "bounded" and BOUNDED_BY_ROWS and table.is_cuda and idx.dim() == 2 and table.shape[-1] <= 6
+        by_rows = (kind == "bounded" and BOUNDED_BY_ROWS and table.is_cuda and idx.dim() == 2 and table.shape[-1] <= 7
                    and 2 * idx.shape[0] >= table.shape[0] > 0)
         src = table
         if by_rows:

@@ -612,7 +612,7 @@ def test_fused_distortion_loss_equals_reference_expression(sb, shape):
     assert outs[0][1].shape == d0.shape
 
 
-@pytest.mark.parametrize("n,metric", [(2, "finf"), (3, "fone"), (4, "riem"), (5, "fmin"), (6, "wsum")])
+@pytest.mark.parametrize("n,metric", [(2, "finf"), (3, "fone"), (4, "riem"), (5, "fmin"), (6, "wsum"), (7, "riem")])
 def test_bounded_by_rows_equals_per_pair_bounded_kernels_and_oracle(sb, n, metric):
     """Bounded domain on the table path with a dense batch: inverse Cayley transform once per table row
     (sympa_bounded_rows_to_upper), upper-half kernels on the pairs, gradient mapped back per row
