@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference); the
 output files are committed so the GPU box never needs the reference tree.
 
-    python oracle/gen_golden.py            # rewrites tests/golden/
+    python oracle/gen_golden.py            # writes the round-2 additions (n = 1, 7, 8, 9; optim.npz)
+    python oracle/gen_golden.py --all      # rewrites all of tests/golden/
 
 What is stored, per (manifold kind, n, input regime):
   z1, z2              inputs (b, 2, n, n) float64
@@ -12,7 +13,8 @@ What is stored, per (manifold kind, n, input regime):
   g1_<metric>, g2_<metric>   autograd gradients of sum(go * dist) wrt z1 / z2 (raw, unsymmetrised)
   gw_wsum, wsum_w     wsum weights used and their gradient
   go                  the upstream gradient used
-plus building blocks (cayley, inverse cayley, complex inverse, Takagi values) in blocks.npz.
+plus building blocks (cayley, inverse cayley, complex inverse, Takagi values) in blocks.npz and the
+optimizer-side manifold functions (egrad2rgrad, projx, retr) in optim.npz.
 """
 import os
 import sys
@@ -45,21 +47,13 @@ def make_inputs(kind, n, regime, b, seed):
     return z1, z2
 
 
-def main():
-    import_reference()
-    from sympa.manifolds import UpperHalfManifold, BoundedDomainManifold
-    from sympa.manifolds.metrics import MetricType
-    from sympa.math import csym_math as sm
-    from sympa.math.cayley_transform import cayley_transform, inverse_cayley_transform
-    from sympa.math.takagi_factorization import TakagiFactorization
-
-    torch.set_default_dtype(torch.float64)
-    os.makedirs(OUT, exist_ok=True)
-    b = 12
-    seed = 1000
+def gen_pairs(ns, seed, sympa_mods, b=12):
+    """dist / vvd / gradient goldens for upper + bounded at the matrix sizes `ns`; seeds seed+1, seed+2, ... in
+    (kind, n, regime) order."""
+    UpperHalfManifold, BoundedDomainManifold, MetricType, sm, cayley_transform = sympa_mods
     for kind in ("upper", "bounded"):
         cls = UpperHalfManifold if kind == "upper" else BoundedDomainManifold
-        for n in (2, 3, 4, 5, 6, 10):
+        for n in ns:
             for regime in ("init", "mid", "spread"):
                 seed += 1
                 z1, z2 = make_inputs(kind, n, regime, b, seed)
@@ -71,7 +65,7 @@ def main():
                 for mname in METRIC_NAMES:
                     man = cls(dims=n, metric=MetricType.from_str(mname))
                     if mname == "wsum":
-                        w = torch.linspace(-0.4, 1.3, n).reshape(1, n)
+                        w = torch.linspace(-0.4, 1.3, n).reshape(1, n) if n > 1 else torch.tensor([[0.7]])
                         if n >= 3:
                             w[0, 1] = 0.0      # relu'(0) = 0 in torch
                         man.metric.weights.data = w.clone()
@@ -96,6 +90,60 @@ def main():
                         rec["gw_wsum"] = man.metric.weights.grad.numpy()
                 np.savez_compressed(os.path.join(OUT, f"{kind}_n{n}_{regime}.npz"), **rec)
                 print(kind, n, regime, "dist_riem[:3] =", rec["dist_riem"][:3])
+    return seed
+
+
+def gen_optim(sympa_mods):
+    """Optimizer-side functions of the unmodified reference (the RiemannianSGD row update calls them:
+    geoopt RSGD -> manifold.egrad2rgrad, manifold.retr -> projx): UpperHalfManifold.egrad2rgrad / projx / retr
+    (sympa/manifolds/upper_half.py:25-66, siegel_manifold.py:74-87) and BoundedDomainManifold.egrad2rgrad
+    (bounded_domain.py:41-53).  BoundedDomainManifold.projx / retr crash in the reference as shipped
+    and cannot be pinned.  Inputs include rows whose update leaves the manifold (projection active)."""
+    UpperHalfManifold, BoundedDomainManifold, MetricType, sm, cayley_transform = sympa_mods
+    rec = {}
+    g = torch.Generator().manual_seed(4242)
+    for n in (2, 3, 4, 6, 10):
+        up = UpperHalfManifold(dims=n, metric=MetricType.from_str("riem"))
+        bd = BoundedDomainManifold(dims=n, metric=MetricType.from_str("riem"))
+        z = so.upper_spread(10, n, generator=g, scale=0.4)
+        u = torch.randn(10, 2, n, n, generator=g)                      # raw (unsymmetrised) Euclidean gradient
+        us = sm.to_symmetric(u)
+        rec[f"upper_z_n{n}"] = z.numpy()
+        rec[f"upper_u_n{n}"] = u.numpy()
+        rec[f"upper_egrad2rgrad_n{n}"] = up.egrad2rgrad(z, u).numpy()
+        rec[f"upper_egrad2rgrad_sym_n{n}"] = up.egrad2rgrad(z, us).numpy()
+        # a big step: some imaginary parts lose positive definiteness, projx clamps their spectrum
+        step = -2.5 * up.egrad2rgrad(z, us)
+        rec[f"upper_step_n{n}"] = step.numpy()
+        rec[f"upper_retr_n{n}"] = up.retr(z, step).numpy()
+        rec[f"upper_projx_n{n}"] = up.projx(z + step).numpy()
+        small = -1e-3 * up.egrad2rgrad(z, us)
+        rec[f"upper_retr_small_n{n}"] = up.retr(z, small).numpy()
+        zb = sm.to_symmetric(cayley_transform(z))
+        rec[f"bounded_z_n{n}"] = zb.numpy()
+        rec[f"bounded_egrad2rgrad_n{n}"] = bd.egrad2rgrad(zb, u).numpy()
+        rec[f"bounded_egrad2rgrad_sym_n{n}"] = bd.egrad2rgrad(zb, us).numpy()
+    np.savez_compressed(os.path.join(OUT, "optim.npz"), **rec)
+    print("wrote optim.npz")
+
+
+def main():
+    import_reference()
+    from sympa.manifolds import UpperHalfManifold, BoundedDomainManifold
+    from sympa.manifolds.metrics import MetricType
+    from sympa.math import csym_math as sm
+    from sympa.math.cayley_transform import cayley_transform, inverse_cayley_transform
+    from sympa.math.takagi_factorization import TakagiFactorization
+
+    torch.set_default_dtype(torch.float64)
+    os.makedirs(OUT, exist_ok=True)
+    mods = (UpperHalfManifold, BoundedDomainManifold, MetricType, sm, cayley_transform)
+    if "--all" in sys.argv:                      # the round-1 set (bit-identical when regenerated)
+        gen_pairs((2, 3, 4, 5, 6, 10), 1000, mods)
+    gen_pairs((1, 7, 8, 9), 2000, mods)          # round 2: the sizes the first set skipped
+    gen_optim(mods)
+    if "--all" not in sys.argv:
+        return
 
     # building blocks
     g = torch.Generator().manual_seed(7)

@@ -717,6 +717,37 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.num_rows; r += stride) {
     const double* g = a.grad + r * PER;
     double* p = a.table + r * PER;
+    double x[T], y[T];
+    if (KIND == kBounded) {
+      // the bounded update needs the gradient block as it is (bounded_rsgd_row): full, not symmetrised
+      double gf[PER];
+      bool any = false;
+      if (REG) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) gf[e] = __ldg(g + e);
+#pragma unroll
+        for (int e = 0; e < PER; ++e) any = any || (gf[e] != 0.0);
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < PER; ++e) {
+          gf[e] = __ldg(g + e);
+          any = any || (gf[e] != 0.0);
+        }
+      }
+      if (!any) continue;
+      if (a.zero_grad) {
+        double* gw = const_cast<double*>(g);
+#pragma unroll 4
+        for (int e = 0; e < PER; ++e) gw[e] = 0.0;
+      }
+      load_packed<N, REG>(p, x);
+      load_packed<N, REG>(p + N * N, y);
+      const bool m = REG ? reg::bounded_rsgd_row<N>(x, y, gf, gf + N * N, lr) : loc::bounded_rsgd_row<N>(x, y, gf, gf + N * N, lr);
+      moved += m ? 1ull : 0ull;
+      store_full<N, REG>(p, x);
+      store_full<N, REG>(p + N * N, y);
+      continue;
+    }
     double gx[T], gy[T];
     load_packed<N, REG>(g, gx);
     if (KIND != kSpd) load_packed<N, REG>(g + N * N, gy);
@@ -729,16 +760,13 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
 #pragma unroll 4
       for (int e = 0; e < PER; ++e) gw[e] = 0.0;
     }
-    double x[T], y[T];
     load_packed<N, REG>(p, x);
     if (KIND == kSpd) {
       if (REG) reg::spd_rsgd_row<N>(x, gx, lr); else loc::spd_rsgd_row<N>(x, gx, lr);
       store_full<N, REG>(p, x);
     } else {
       load_packed<N, REG>(p + N * N, y);
-      const bool m = (KIND == kBounded)
-                         ? (REG ? reg::bounded_rsgd_row<N>(x, y, gx, gy, lr) : loc::bounded_rsgd_row<N>(x, y, gx, gy, lr))
-                         : (REG ? reg::upper_rsgd_row<N>(x, y, gx, gy, lr) : loc::upper_rsgd_row<N>(x, y, gx, gy, lr));
+      const bool m = REG ? reg::upper_rsgd_row<N>(x, y, gx, gy, lr) : loc::upper_rsgd_row<N>(x, y, gx, gy, lr);
       moved += m ? 1ull : 0ull;
       store_full<N, REG>(p, x);
       store_full<N, REG>(p + N * N, y);

@@ -83,7 +83,9 @@ class FinslerWeightedSumMetric(Metric, torch.nn.Module):  # metrics.py:103-121
     def __init__(self, dims):
         torch.nn.Module.__init__(self)
         Metric.__init__(self, dims)
-        self.weights = torch.nn.parameter.Parameter(torch.ones((1, dims)))
+        # float64 like the embedding table and the scale: the reference gets that from the global default dtype it
+        # sets in sympa/config.py:17-18; this package does not touch the global default
+        self.weights = torch.nn.parameter.Parameter(torch.ones((1, dims), dtype=torch.float64))
 
     def compute_metric(self, v, keepdim=False):
         return torch.sum(torch.relu(self.weights) * v, dim=-1, keepdim=keepdim)

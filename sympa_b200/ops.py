@@ -184,22 +184,42 @@ class _DistFn(torch.autograd.Function):
         return g1, g2, gw, None, None
 
 
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def bounded_by_rows(kind, n, num_pairs, num_rows, sync_grad):
+    """Route choice of the bounded domain on the table path (see _TableDistFn).  With sync_grad in a
+    multi-process group the choice must not depend on rank-local state - the ranks put their result into ONE
+    all-reduced buffer, and the by-rows route accumulates the gradient with respect to the TRANSFORMED rows -
+    so there it depends on (kind, n) only; a single process also looks at how densely the batch covers the table."""
+    if not (BOUNDED_BY_ROWS and kind == "bounded" and n <= 7 and num_rows > 0):
+        return False
+    if sync_grad and _world_size() > 1:
+        return True
+    return 2 * num_pairs >= num_rows
+
+
 class _TableDistFn(torch.autograd.Function):
     """dist(table[idx[:,0]], table[idx[:,1]]) with the gather fused into the forward kernel and the
     gather backward (dense index_put in the reference, sympa/embeddings.py:29-34) fused into an
     atomic scatter-add."""
 
     @staticmethod
-    def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False):
+    def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False, by_rows=None):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         # bounded domain, batch covering the table densely: the inverse Cayley transform is applied once per
         # table row (sympa_bounded_rows_to_upper) and the pairs run the upper-half kernels on the result
         # (break-even in flops is 2 pairs per row.  Only for n <= 7, where the row kernels are the unrolled register
         # code: the rolled local-memory row kernels of the larger sizes measured far slower than they save -
         # bounded n = 10 18.9 -> 8.2 M pairs/s on a 2^20-row table)
-        by_rows = (kind == "bounded" and BOUNDED_BY_ROWS and table.is_cuda and idx.dim() == 2 and table.shape[-1] <= 7
-                   and 2 * idx.shape[0] >= table.shape[0] > 0)
+        if by_rows is None:
+            by_rows = table.is_cuda and idx.dim() == 2 and bounded_by_rows(kind, table.shape[-1], idx.shape[0],
+                                                                           table.shape[0], sync_grad)
+        by_rows = bool(by_rows) and kind == "bounded"
         src = table
+        t = None
         if by_rows:
             t = _require(table, "table").detach()
             src = torch.empty_like(t)
@@ -209,7 +229,8 @@ class _TableDistFn(torch.autograd.Function):
         kk = "upper" if by_rows else kind
         dist, vvd, saved = forward_raw(kk, metric, table=src, idx=idx, wsum_w=wsum_w, want_grad=need)
         ctx.kind, ctx.metric, ctx.tshape, ctx.sync_grad, ctx.by_rows = kk, metric, table.shape, sync_grad, by_rows
-        ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None, table.detach() if by_rows else None)
+        # (the contiguous copy `t`, not `table`: the backward hands its raw pointer to the row kernel)
+        ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None, t)
         ctx.mark_non_differentiable(vvd)
         return dist, vvd
 
@@ -220,15 +241,10 @@ class _TableDistFn(torch.autograd.Function):
         grad_dist = _require(grad_dist, "grad_dist")
         b, n = vvd.shape
         dev = vvd.device
-        if b == 0:
-            gt = torch.zeros(ctx.tshape, dtype=torch.float64, device=dev)
-            gw = None if wsum_w is None else torch.zeros_like(wsum_w)
-            if ctx.sync_grad:       # the other ranks are in the collective: take part
-                _allreduce_avg(gt)
-                if gw is not None:
-                    _allreduce_avg(gw)
-            return gt, None, gw, None, None, None
         with torch.cuda.device(dev):
+            # every decision below depends on (kind, n, rows, sync_grad) only, never on the local batch: with
+            # sync_grad all ranks must enter the same collectives on buffers of the same size, a rank with an
+            # empty shard included
             gt = torch.empty(ctx.tshape, dtype=torch.float64, device=dev)     # written, not accumulated (overwrite=1)
             gw = None
             w_flat = None
@@ -241,14 +257,20 @@ class _TableDistFn(torch.autograd.Function):
                 # data-parallel backward: scatter into the packed gradient table, all-reduce (average) THAT - the
                 # one collective of the path, on 62 % of the dense bytes at n = 4 - then write the dense rows
                 need = lib.sympa_backward_workspace_bytes(k, n, rows)
-                _lib.check(lib.sympa_table_grad_scatter(k, n, m, b, _ptr(grad_dist), _ptr(saved), rows, _ptr(idx.contiguous()),
-                                                        _ptr(vvd), _ptr(w_flat), _ptr(gw), _ptr(ws), ws_bytes, _stream()))
+                if b > 0:
+                    _lib.check(lib.sympa_table_grad_scatter(k, n, m, b, _ptr(grad_dist), _ptr(saved), rows, _ptr(idx.contiguous()),
+                                                            _ptr(vvd), _ptr(w_flat), _ptr(gw), _ptr(ws), ws_bytes, _stream()))
+                else:
+                    ws[: need // 8].zero_()
                 _allreduce_avg(ws[: need // 8])
                 _lib.check(lib.sympa_table_grad_expand(k, n, rows, _ptr(ws), _ptr(gt), 1, _stream()))
             else:
-                _lib.check(lib.sympa_dist_backward_table(
-                    k, n, m, b, _ptr(grad_dist), _ptr(saved), _ptr(gt), rows, _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat),
-                    _ptr(gw), _ptr(ws), ws_bytes, 1, _stream()))
+                if b > 0:
+                    _lib.check(lib.sympa_dist_backward_table(
+                        k, n, m, b, _ptr(grad_dist), _ptr(saved), _ptr(gt), rows, _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat),
+                        _ptr(gw), _ptr(ws), ws_bytes, 1, _stream()))
+                else:
+                    gt.zero_()
                 if ctx.sync_grad:
                     _allreduce_avg(gt)
             if ctx.sync_grad and gw is not None:
@@ -259,7 +281,7 @@ class _TableDistFn(torch.autograd.Function):
                 gt = gz
         if gw is not None:
             gw = gw.reshape(wsum_w.shape)
-        return gt, None, gw, None, None, None
+        return gt, None, gw, None, None, None, None
 
 
 def dist(kind, metric, z1, z2, wsum_w=None):
@@ -278,11 +300,12 @@ def _allreduce_avg(t):
             t.div_(dist.get_world_size())
 
 
-def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False):
+def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False, by_rows=None):
     """sync_grad=True: the backward also averages the table gradient (and dL/dw of wsum) over the ranks of
     the default process group - on the packed gradient table where there is one - so the caller must NOT
-    all-reduce table.grad again."""
-    return _TableDistFn.apply(table, idx, wsum_w, kind, metric, bool(sync_grad))
+    all-reduce table.grad again.  Every rank of the group must make the call (an empty local batch included).
+    by_rows: force / forbid the bounded-domain row route (None: bounded_by_rows decides)."""
+    return _TableDistFn.apply(table, idx, wsum_w, kind, metric, bool(sync_grad), by_rows)
 
 
 def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsum_w=None, grad_wsum_w=None,

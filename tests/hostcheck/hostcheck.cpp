@@ -219,7 +219,7 @@ extern "C" int hostcheck_run(int variant, int kind, int n, int metric, int64_t b
         NS::pack_sym<N>(p + N * N, y);                                                                       \
         NS::pack_sym<N>(g, gx);                                                                              \
         NS::pack_sym<N>(g + N * N, gy);                                                                      \
-        projected += (kind == kBounded ? NS::bounded_rsgd_row<N>(x, y, gx, gy, lr)                           \
+        projected += (kind == kBounded ? NS::bounded_rsgd_row<N>(x, y, g, g + N * N, lr)                     \
                                        : NS::upper_rsgd_row<N>(x, y, gx, gy, lr)) ? 1 : 0;                    \
         for (int i = 0; i < N; ++i)                                                                          \
           for (int j = 0; j < N; ++j) {                                                                      \

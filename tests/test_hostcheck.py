@@ -90,6 +90,8 @@ def test_cooperative_templates_match_reference_golden(hostcheck, path):
     """namespace sympa::coop (the warp-cooperative shared-memory kernel, n >= 5 on the GPU) with the
     lanes of a group emulated one after the other; shared memory is poisoned before every pair."""
     kind, n, regime, r = load_golden(path)
+    if n < 2:
+        pytest.skip("the cooperative templates start at n = 2 (the library never uses them below n = 7)")
     for m in METRICS:
         w = r["wsum_w"] if m == "wsum" else None
         d, v, g1, g2, st = hostcheck(2, kind, n, m, r["z1"], r["z2"], w)
