@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4] [--kind upper]
 
-Workload (config.workload): BASELINE.json configs[4] 'distance microbench' - a table of 2^20 random
-points, B index pairs per GPU per step, manifold `--kind` with n x n matrices, metric riem, forward
-+ backward through the distortion loss (sympa/losses.py:16-19).  One step = gather -> dist ->
-loss -> backward -> scatter-add into the dense table gradient (+ NCCL all-reduce of that gradient
-when N > 1).  `value` is measured with everything resident in HBM; `e2e` runs the same step through
-the public manifold API with the step's inputs (index pairs, graph distances) copied from pinned
-host memory and the loss read back, inside the timed region.
+Workload (config.workload) = BASELINE.json configs[4], the distance microbench: a table of 2^20 random points
+and ONE BATCH OF 64M (2^26) random index pairs per step, manifold `--kind` with n x n matrices, forward +
+backward through the distortion loss (sympa/losses.py:16-19).  The batch is sharded over the N ranks (strong
+scaling: 2^26 / N pairs per GPU and step); a rank works through its shard in chunks of 2^23 pairs, each chunk
+one call of the public API (gather -> dist -> loss -> backward -> scatter-add into the table gradient), and the
+step ends with the one collective of the path, the NCCL all-reduce (average) of the table gradient.
+`value` is measured with everything resident in HBM; `e2e` runs the same step with every chunk's index pairs
+and graph distances copied from pinned host memory and the loss read back, inside the timed region.
+A second record, `n10`, repeats the measurement for upper / fmin / n = 10 (the other size BASELINE.json's metric
+names) on a smaller batch.
 """
 import argparse
 import json
@@ -22,26 +25,34 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
-    # keep NCCL's version banner (printed to STDOUT at VERSION and WARN level) out of the way: rank 0 prints
-    # ONE JSON line.  An unrecognised level means "no logging" to NCCL; INFO / TRACE set by the user are kept.
-    os.environ["NCCL_DEBUG"] = "NONE"
 
 import torch  # noqa: E402
 
+GLOBAL_PAIRS = 1 << 26          # BASELINE.json configs[4]: 64M random pairs per batch
+CHUNK_PAIRS = 1 << 23           # pairs per API call (saved unit gradients of a chunk: 2.7 GB at n = 4)
+N10_GLOBAL_PAIRS = 1 << 23      # batch of the n = 10 side record (a step is ~0.1-0.2 s on one GPU)
 
-def default_pairs(n):
-    """pairs per GPU per step: BASELINE.json's 64M-pair batch over 8 GPUs (2^23 per GPU) where the saved unit
-    gradients fit comfortably, smaller for the large matrix sizes (a step is still >= 25 ms there)."""
-    return (1 << 23) if n <= 4 else ((1 << 20) if n <= 6 else (1 << 18))
+
+def chunk_pairs_for(n):
+    return CHUNK_PAIRS if n <= 4 else ((1 << 21) if n <= 6 else (1 << 19))
 
 
 def algorithmic_bytes_per_pair(kind, n):
-    """read two rows, accumulate two gradient rows, two int64 indices, vvd out, dist
+    """SURVEY.md 8(d), whole step: read two rows, accumulate two gradient rows, two int64 indices, vvd out, dist
     out, upstream gradient in."""
     if kind == "spd":
         return 32 * n * n + 8 * n + 32
     return 64 * n * n + 8 * n + 32
+
+
+def kernel_bytes_per_pair(kind, n):
+    """the forward + unit-gradient kernel ALONE: two rows in, two index words, dist + vvd out, and the saved unit
+    gradients out (packed lower triangles for the register kernels, full blocks for the cooperative ones)"""
+    blocks = 1 if kind == "spd" else 2
+    rows_in = 2 * blocks * n * n * 8
+    packed = n <= {"upper": 6, "bounded": 7, "spd": 10}[kind]
+    state = 2 * blocks * (n * (n + 1) // 2 if packed else n * n) * 8
+    return rows_in + state + 16 + 8 * n + 8
 
 
 def lean_flops_per_pair(n):
@@ -51,8 +62,8 @@ def lean_flops_per_pair(n):
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+        return json.load(open(p)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -89,7 +100,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -98,6 +109,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(names, f[5:9]):
@@ -105,18 +117,22 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measure_fp64_peak(dev):
-    """attainable FP64 FMA rate of this GPU in TFLOP/s (sympa_probe_fp64, best of 5, CUDA events)."""
+def measure_fp64_peak(dev, local):
+    """attainable FP64 FMA rate of this GPU in TFLOP/s (sympa_probe_fp64: pure DFMA chains, best of 6, CUDA events),
+    with the SM clock sampled while the probe runs"""
     from sympa_b200 import _lib
     lib = _lib.load()
     out = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     iters = 1 << 16
     best = 0.0
-    for _ in range(6):
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(12):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         flops = lib.sympa_probe_fp64(iters, out.data_ptr(), stream)
@@ -124,7 +140,8 @@ def measure_fp64_peak(dev):
         torch.cuda.synchronize()
         if flops > 0:
             best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
-    return best
+    clocks = sampler.stop()
+    return best, clocks
 
 
 def make_table(kind, n, rows, device, seed):
@@ -148,229 +165,375 @@ def make_table(kind, n, rows, device, seed):
 
 
 def make_pairs(rows, b, device, seed):
+    """src ~ U{0..N-1}, dst != src, graph distance ~ U{1..20}; distances as uint8 - what
+    preprocess.py:118-126 produces are small integers."""
     g = torch.Generator(device=device).manual_seed(seed)
     src = torch.randint(0, rows, (b,), device=device, generator=g)
     dst = (src + 1 + torch.randint(0, rows - 1, (b,), device=device, generator=g)) % rows   # src != dst
-    gd = torch.randint(1, 21, (b,), device=device, generator=g).double()
+    gd = torch.randint(1, 21, (b,), device=device, generator=g, dtype=torch.uint8)
     return torch.stack((src, dst), 1).contiguous(), gd
 
 
-def distortion_loss(graph_dist, manifold_dist):
-    """sympa/losses.py:16-19.  GPU legs: the package's AverageDistortionLoss (same expression, one kernel forward
-    and one backward on CUDA float64 vectors); CPU legs (baseline / reference arm): the reference's torch ops."""
-    if manifold_dist.is_cuda:
-        from sympa_b200.losses import AverageDistortionLoss
-        return AverageDistortionLoss().calculate_loss(graph_dist, manifold_dist)
+def reference_loss(graph_dist, manifold_dist):
+    """sympa/losses.py:16-19, the reference's torch expression"""
     return torch.abs(torch.pow(manifold_dist / graph_dist, 2) - 1).sum()
 
 
-def run_ours(args):
-    import torch.distributed as dist
-    from sympa_b200 import BoundedDomainManifold, MetricType, SymmetricPositiveDefinite, UpperHalfManifold, ops
-    from sympa_b200 import distributed as sd
-
-    rank, world, local = sd.init_process_group()
-    assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
-    dev = torch.device("cuda", local)
-    kind, n = args.kind, args.n
-    rows = args.rows
-    b = args.pairs if args.pairs else default_pairs(n)
+def make_manifold(kind, n, metric, dev):
+    from sympa_b200 import BoundedDomainManifold, MetricType, SymmetricPositiveDefinite, UpperHalfManifold
     if kind == "spd":
-        man = SymmetricPositiveDefinite().to(dev)
-    else:
-        man = {"upper": UpperHalfManifold, "bounded": BoundedDomainManifold}[kind](
-            dims=n, metric=MetricType.from_str(args.metric)).to(dev)
-    table = make_table(kind, n, rows, dev, seed=1).requires_grad_(True)     # replicated on every rank
-    idx, gd = make_pairs(rows, b, dev, seed=100 + rank)                       # each rank its own shard
-    scale = 1.0
+        return SymmetricPositiveDefinite().to(dev)
+    return {"upper": UpperHalfManifold, "bounded": BoundedDomainManifold}[kind](
+        dims=n, metric=MetricType.from_str(metric)).to(dev)
 
-    def step_resident():
-        table.grad = None
-        d = man.dist_from_table(table, idx, sync_grad=world > 1)   # the all-reduce (average) runs inside the backward,
-        loss = distortion_loss(gd, d * scale)                       # on the packed gradient table
-        loss.backward()
-        return loss
 
-    # host-resident inputs for the e2e leg
-    idx_h = idx.to(torch.int32).cpu().pin_memory()    # node ids as int32 on the host, widened on the device by the feeder
-    gd_h = gd.cpu().pin_memory()
-    loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
+def our_launches_per_chunk(kind, n, rows, b, dev, world):
+    """kernels of libsympa_b200.so one chunk launches through the public API: forward + unit gradients, loss forward
+    and backward, table-gradient backward (packed scatter + expansion, or the direct scatter); the bounded domain
+    by rows adds its two row kernels.  torch's own fill / add kernels are not counted."""
+    from sympa_b200 import ops
+    by_rows = ops.bounded_by_rows(kind, n, b, rows, world > 1)
+    kk = "upper" if by_rows else kind
+    packed = ops.backward_workspace_for(kk, n, rows, dev)[1] > 0 and (2 * b >= rows or world > 1)
+    return 1 + 2 + (2 if packed else 1) + (2 if by_rows else 0)
 
+
+def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, local, dev, per_kernel=True, fused=True,
+            e2e=True):
+    """pairs/s of one configuration: resident step, per-kernel times, fused step, end-to-end step."""
+    import torch.distributed as dist
+    from sympa_b200 import _lib, ops
+    from sympa_b200 import distributed as sd
     from sympa_b200.feeder import PairFeeder
-    feeder = PairFeeder(dev)
+    from sympa_b200.losses import AverageDistortionLoss
 
-    def step_e2e(more):
-        """One step through the public API with HOST inputs: this step's batch was submitted (pinned ->
-        device, side stream) before the previous step's compute was enqueued, the next one is submitted
-        here, the loss is read back and the host waits for it."""
-        idx_b, gd_b = feeder.next()
-        if more:
-            feeder.submit(idx_h, gd_h)
-        table.grad = None
-        d = man.dist_from_table(table, idx_b, sync_grad=world > 1)
-        loss = distortion_loss(gd_b, d * scale)
-        loss.backward()
-        feeder.done()
-        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_h[0])
-
-    def run_e2e(steps):
-        feeder.submit(idx_h, gd_h)            # first batch: its copy is exposed, and inside the timed region
-        for s in range(steps):
-            step_e2e(s + 1 < steps)
+    man = make_manifold(kind, n, metric, dev)
+    loss_fn = AverageDistortionLoss()
+    table = make_table(kind, n, rows, dev, seed=1).requires_grad_(True)     # replicated on every rank
+    b_rank = global_pairs // world                                          # this rank's shard of the batch
+    chunk = min(chunk_pairs_for(n), b_rank)
+    n_chunks = -(-b_rank // chunk)
+    idx, gd8 = make_pairs(rows, b_rank, dev, seed=100 + rank)
+    gd = gd8.double()
+    scale = 1.0
+    mk = metric if kind != "spd" else "riem"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, fwd_events=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    def run_chunks(get_chunk):
+        """one step: every chunk through the public API; the table gradient accumulates in table.grad, the one
+        collective of the step follows the last backward (inside it, on the packed gradient table, when the
+        shard is a single chunk)"""
+        table.grad = None
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        for c in range(n_chunks):
+            idx_c, gd_c = get_chunk(c)
+            d = man.dist_from_table(table, idx_c, sync_grad=(world > 1 and n_chunks == 1))
+            loss = loss_fn.calculate_loss(gd_c, d * scale)
+            loss.backward()
+            total += loss.detach()
+        if world > 1 and n_chunks > 1:
+            sd.allreduce_gradients([table.grad], average=True)
+        return total
+
+    def resident_chunk(c):
+        return idx[c * chunk:(c + 1) * chunk], gd[c * chunk:(c + 1) * chunk]
+
+    def step_resident():
+        return run_chunks(resident_chunk)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    for _ in range(warmup):
         step_resident()
     ops.check_status(dev)
-
-    # dominant kernel (forward + unit gradients) timed alone inside the same loop shape
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
-    ms_total = timed(step_resident, args.steps)
+    time.sleep(0.2)
+    ms_total = timed(step_resident, steps)
     clocks = sampler.stop()
-    ms_step = ms_total / args.steps
-    value = world * b * args.steps / (ms_total * 1e-3)
+    res = {"value": global_pairs * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "clocks": clocks,
+           "pairs_per_gpu_per_step": b_rank, "chunk_pairs": chunk, "chunks_per_step": n_chunks}
+    lpc = our_launches_per_chunk(kind, n, rows, chunk, dev, world)
+    res["gpu_launches"] = lpc * n_chunks * steps
+    res["launches_per_chunk"] = lpc
 
-    # per-kernel durations with CUDA events on the launching (current) stream
-    fwd_ms, bwd_ms = [], []
-    for _ in range(min(args.steps, 10)):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        with torch.no_grad():
-            ev[0].record()
-            dd, vv, saved = ops.forward_raw(kind, args.metric if kind != "spd" else "riem", table=table.detach(), idx=idx,
-                                            wsum_w=None, want_grad=True)
-            ev[1].record()
-        g = torch.ones_like(dd)
-        gt = torch.empty_like(table)
-        from sympa_b200 import _lib
-        lib = _lib.load()
+    lib = _lib.load()
+    if per_kernel:   # the kernels of one chunk timed alone, CUDA events on the launching (current) stream
+        fwd_ms, bwd_ms = [], []
+        ci, cg = resident_chunk(0)
+        cb = ci.shape[0]
         ws, ws_bytes = ops.backward_workspace_for(kind, n, rows, dev)
-        ev[2].record()   # the backward of the table path as the autograd Function issues it (workspace, overwrite)
-        _lib.check(lib.sympa_dist_backward_table(_lib.KIND[kind], n, _lib.METRIC["riem"], b, g.data_ptr(), saved.data_ptr(),
-                                                 gt.data_ptr(), rows, idx.data_ptr(), None, None, None,
-                                                 None if ws is None else ws.data_ptr(), ws_bytes, 1,
-                                                 torch.cuda.current_stream().cuda_stream))
-        ev[3].record()
-        torch.cuda.synchronize()
-        fwd_ms.append(ev[0].elapsed_time(ev[1]))
-        bwd_ms.append(ev[2].elapsed_time(ev[3]))
-        del saved, dd, vv, gt
-    fwd = statistics.mean(fwd_ms)
-    bwd = statistics.mean(bwd_ms)
+        gt = torch.empty_like(table)
+        for _ in range(min(steps, 10)):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            with torch.no_grad():
+                ev[0].record()
+                dd, vv, saved = ops.forward_raw(kind, mk, table=table.detach(), idx=ci, wsum_w=None, want_grad=True)
+                ev[1].record()
+            g1 = torch.ones_like(dd)
+            ev[2].record()   # the backward of the table path as the autograd Function issues it (workspace, overwrite)
+            _lib.check(lib.sympa_dist_backward_table(_lib.KIND[kind], n, _lib.METRIC["riem"], cb, g1.data_ptr(),
+                                                     saved.data_ptr(), gt.data_ptr(), rows, ci.data_ptr(), None, None, None,
+                                                     None if ws is None else ws.data_ptr(), ws_bytes, 1,
+                                                     torch.cuda.current_stream().cuda_stream))
+            ev[3].record()
+            torch.cuda.synchronize()
+            fwd_ms.append(ev[0].elapsed_time(ev[1]))
+            bwd_ms.append(ev[2].elapsed_time(ev[3]))
+            del saved, dd, vv
+        del gt
+        res["kernel_ms"] = statistics.mean(fwd_ms)
+        res["backward_ms"] = statistics.mean(bwd_ms)
+        res["kernel_pairs"] = cb
 
-    # fused single-launch step (extension: on-device loss), for comparison
-    gt = torch.zeros_like(table)
-    loss_out = torch.zeros(1, dtype=torch.float64, device=dev)
+    if fused:    # one launch per chunk (on-device loss): sympa_distortion_step
+        gtab = torch.zeros_like(table)
+        loss_out = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def step_fused():
-        gt.zero_()
-        loss_out.zero_()
-        ops.distortion_step(kind, args.metric if kind != "spd" else "riem", table.detach(), idx, gd, scale, gt,
-                            loss_out=loss_out)
-    for _ in range(3):
-        step_fused()
-    ms_fused = timed(step_fused, args.steps) / args.steps
-    del gt
+        def step_fused():
+            gtab.zero_()
+            loss_out.zero_()
+            for c in range(n_chunks):
+                ic, gc = resident_chunk(c)
+                ops.distortion_step(kind, mk, table.detach(), ic, gc, scale, gtab, loss_out=loss_out)
+            if world > 1:
+                sd.allreduce_gradients([gtab], average=True)
+        for _ in range(2):
+            step_fused()
+        k = max(2, steps // 2)
+        ms_fused = timed(step_fused, k) / k
+        res["fused_step"] = {"pairs_per_s": global_pairs / (ms_fused * 1e-3), "ms_per_step": ms_fused,
+                             "launches_per_chunk": 1}
+        del gtab
 
-    # e2e
-    run_e2e(3)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    run_e2e(args.steps)
-    t1.record()
-    barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
-    e2e_value = world * b * args.steps / (ms_e2e * 1e-3)
+    if e2e:
+        # host-resident inputs: node ids as int32, graph distances as uint8 (9 bytes per pair on the wire), widened
+        # on the device by the feeder; every chunk of every step crosses PCIe inside the timed region
+        idx_h = idx.to(torch.int32).cpu().pin_memory()
+        gd_h = gd8.cpu().pin_memory()
+        loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
+        feeder = PairFeeder(dev)
+
+        def submit(c):
+            feeder.submit(idx_h[c * chunk:(c + 1) * chunk], gd_h[c * chunk:(c + 1) * chunk])
+
+        def step_e2e(more_steps):
+            first = [True]
+
+            def get(c):
+                if not first[0]:
+                    feeder.done()           # the kernels that read the previous chunk are enqueued
+                first[0] = False
+                ic, gc = feeder.next()
+                if c + 1 < n_chunks:        # the copy of the next chunk overlaps this chunk's compute
+                    submit(c + 1)
+                elif more_steps:
+                    submit(0)
+                return ic, gc
+            total = run_chunks(get)
+            feeder.done()
+            loss_h.copy_(total.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(loss_h[0])
+
+        def run_e2e(k):
+            submit(0)                       # first chunk: its copy is exposed, and inside the timed region
+            for s in range(k):
+                step_e2e(s + 1 < k)
+
+        run_e2e(2)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        run_e2e(steps)
+        t1.record()
+        barrier()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+        res["e2e"] = {"value": global_pairs * steps / (ms_e2e * 1e-3), "unit": "pairs/s",
+                      "h2d_bytes_per_step": int((idx_h.numel() * idx_h.element_size() + gd_h.numel() * gd_h.element_size()) * world),
+                      "d2h_bytes_per_step": 8 * world,
+                      "ms_per_step": ms_e2e / steps,
+                      "how": "per step and rank: every chunk = manifold.dist_from_table + AverageDistortionLoss + backward "
+                             "through the public API; the chunk's index pairs (int32 on the host, widened on the device) and "
+                             "graph distances (uint8 on the host) are copied from pinned host memory by "
+                             "sympa_b200.feeder.PairFeeder (the copy of chunk k+1 overlaps the compute of chunk k on a side "
+                             "stream; the first copy is exposed), the step's loss is read back and the host waits for it"}
+        del idx_h, gd_h
     ops.check_status(dev)
+    del table, idx, gd
+    torch.cuda.empty_cache()
+    return res
 
-    peaks, peak_kind = load_peaks()
-    fp64_peak = measure_fp64_peak(dev)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+
+def roofline_of(kind, n, res, fp64_peak, fp64_clocks, peaks, peak_src, rows):
+    """roofline object of the dominant kernel (forward + unit gradients) from its live-timed duration"""
+    b = res["kernel_pairs"]
+    k_s = res["kernel_ms"] * 1e-3
+    lean_tf = lean_flops_per_pair(n) * b / k_s / 1e12
+    kb = kernel_bytes_per_pair(kind, n) * b
+    step_b = res["pairs_per_gpu_per_step"]
+    step_s = res["ms_per_step"] * 1e-3
+    coop = n > {"upper": 6, "bounded": 7, "spd": 10}[kind]
+    kname = (f"coop_kernel<{n},{kind},fwd+unit-grad>" if coop else f"pair_kernel<{n},{kind},fwd+unit-grad>")
+    fp64_bound = n >= 3
+    traffic = scatter = None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(f"{kind}_n{n}_fwdsave")
+        tj = json.load(open(tpath))
+        rec = tj.get(f"{kind}_n{n}_fwdsave")
         if rec:
             traffic = rec["bytes_per_pair"] * b     # ncu dram bytes per pair x pairs of one launch
-    scatter = None
-    if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(f"{kind}_n{n}_backward")
-        if rec:   # the backward of a step: its DRAM traffic (ncu) over its live-timed duration
+        rec = tj.get(f"{kind}_n{n}_backward")
+        if rec:   # the backward of a chunk: its DRAM traffic (ncu) over its live-timed duration
             sbytes = rec["scatter_bytes_per_pair"] * b + rec["expand_bytes_per_row"] * rows
-            scatter = {"kernel": rec["kernel"], "bound": "hbm", "traffic": sbytes,
-                       "achieved": round(sbytes / (bwd * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": round(sbytes / (bwd * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                       "note": "DRAM bytes measured by ncu at 2^20 pairs / 2^20 rows (per pair: random read-modify-write of "
-                               "packed table-gradient rows that do not fit L2 + the packed saved state; per row: memset, "
-                               "read and dense write of the expansion), scaled to this run's pairs and rows - not "
-                               "algorithmic bytes"}
-    abytes = algorithmic_bytes_per_pair(kind, n) * b
-    achieved = abytes / (fwd * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": f"pair_kernel<{n},{kind},fwd+unit-grad>", "achieved": round(achieved, 2),
-        "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-        "traffic": traffic, "traffic_source": "ncu --set full capture, see profiles/r01_traffic.json",
-        "algorithmic_bytes": abytes, "kernel_ms": round(fwd, 4), "scatter_kernel_ms": round(bwd, 4),
-        "fp64": {"achieved_lean_tflops": round(lean_flops_per_pair(n) * b / (fwd * 1e-3) / 1e12, 3),
-                 "peak_measured_tflops": round(fp64_peak, 2), "peak_nominal_tflops": 37.2,
-                 "frac_of_measured": round(lean_flops_per_pair(n) * b / (fwd * 1e-3) / 1e12 / max(fp64_peak, 1e-9), 4),
-                 "how": "algorithmic flops 100 n^3 per pair (SURVEY 8(d) F_lean) / kernel time; peak = sympa_probe_fp64 "
-                        "(pure DFMA chains) timed with CUDA events in this run"},
-        "note": "n >= 3 is bound by the FP64 pipe (Jacobi sweeps), not HBM: see the fp64 object and profiles/; the "
-                "HBM fraction uses algorithmic bytes 64n^2+8n+32 per pair",
-    }
+            alg = (3 * 16 * n * (n + 1) + 24) * b + 48 * n * n * rows
+            scatter = {"kernel": rec["kernel"], "bound": "hbm", "traffic": sbytes, "algorithmic_bytes": alg,
+                       "achieved": round(alg / (res["backward_ms"] * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": round(alg / (res["backward_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                       "traffic_over_algorithmic": round(sbytes / alg, 3)}
+    fp64 = {"bound": "fp64", "achieved": round(lean_tf, 3), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
+            "frac": round(lean_tf / max(fp64_peak, 1e-9), 4), "peak_nominal": 37.2,
+            "peak_source": "sympa_probe_fp64 (pure DFMA chains) timed with CUDA events in this run - MEASURED_PEAKS.json "
+                           "has no FP64 entry", "peak_clocks": fp64_clocks,
+            "how": "algorithmic flops 100 n^3 per pair (SURVEY.md 8(d) F_lean) x pairs of one launch / kernel time"}
+    hbm = {"bound": "hbm", "achieved": round(kb / k_s / 1e9, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "frac": round(kb / k_s / 1e9 / peaks["hbm_gbs"], 4), "algorithmic_bytes": kb, "peak_source": peak_src,
+           "how": "the kernel's OWN algorithmic bytes (rows in, indices, dist + vvd, saved unit gradients out) / kernel time"}
+    main = dict(fp64 if fp64_bound else hbm)
+    main.update({"kernel": kname, "kernel_ms": round(res["kernel_ms"], 4), "pairs_per_launch": b, "traffic": traffic,
+                 "traffic_source": "ncu --set full capture, profiles/r02_traffic.json" if traffic else None,
+                 "other_bound": hbm if fp64_bound else fp64,
+                 "whole_step": {
+                     "fp64_frac": round(lean_flops_per_pair(n) * step_b / step_s / 1e12 / max(fp64_peak, 1e-9), 4),
+                     "hbm_frac": round(algorithmic_bytes_per_pair(kind, n) * step_b / step_s / 1e9 / peaks["hbm_gbs"], 4),
+                     "how": "F_lean resp. SURVEY.md 8(d) bytes (64n^2+8n+32) x this GPU's pairs of a step / device time of the "
+                            "whole step (forward, loss, backward scatter + expansion, gradient accumulation, collective)"},
+                 "backward_ms": round(res["backward_ms"], 4)})
     if scatter is not None:
-        roofline["scatter"] = scatter
+        main["scatter"] = scatter
+    return main
+
+
+def parity_check(rank, world, dev):
+    """N > 1, inside the warm-up: the table gradient after the in-backward NCCL all-reduce (pairs sharded over the
+    ranks as DistributedSampler does, train.py:105-110) must equal the full-batch gradient of one GPU divided by
+    the number of ranks (DDP averages, train.py:59).  40 960 pairs, upper n = 4 and bounded n = 3 (by-rows route);
+    also a rank with an EMPTY shard joins the collective.  Every rank checks; the verdict is the AND over ranks."""
+    import torch.distributed as dist
+    from sympa_b200 import distributed as sd
+    out = {"ok": True, "max_rel": 0.0, "pairs": 40960, "cases": []}
+    for kind, n, metric in (("upper", 4, "riem"), ("bounded", 3, "fone"), ("upper", 10, "fmin")):
+        rows, pairs = 4096, 40960
+        man = make_manifold(kind, n, metric, dev)
+        table = make_table(kind, n, rows, dev, seed=7)
+        idx, gd8 = make_pairs(rows, pairs, dev, seed=11)          # same batch on every rank
+        gd = gd8.double()
+
+        def grad_of(sel, sync):
+            t = table.clone().requires_grad_(True)
+            d = man.dist_from_table(t, idx[sel].contiguous(), sync_grad=sync)
+            reference_loss(gd[sel], d).backward()
+            return t.grad
+
+        shard = sd.shard_indices(pairs, rank, world, shuffle=True, seed=3).to(dev)
+        avg = grad_of(shard, True)
+        everyone = torch.cat([sd.shard_indices(pairs, r, world, shuffle=True, seed=3) for r in range(world)]).to(dev)
+        full = grad_of(everyone, False) / world
+        rel = float((avg - full).abs().max() / full.abs().max())
+        # ragged: the last rank has nothing this step
+        sel = shard if rank < world - 1 else shard[:0]
+        avg2 = grad_of(sel, True)
+        part = torch.cat([sd.shard_indices(pairs, r, world, shuffle=True, seed=3) for r in range(world - 1)]).to(dev)
+        full2 = grad_of(part, False) / world
+        rel2 = float((avg2 - full2).abs().max() / full2.abs().max())
+        out["cases"].append({"kind": kind, "n": n, "max_rel": rel, "max_rel_empty_rank": rel2})
+        out["max_rel"] = max(out["max_rel"], rel, rel2)
+    out["ok"] = bool(out["max_rel"] < 1e-9)
+    flag = torch.tensor([1.0 if out["ok"] else 0.0, out["max_rel"]], dtype=torch.float64, device=dev)
+    ok = flag[:1].clone()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    mx = flag[1:].clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    out["ok"] = bool(ok.item() > 0.5)
+    out["max_rel"] = float(mx.item())
+    out["how"] = ("dist_from_table(sync_grad=True) on each rank's DistributedSampler shard vs the full-batch gradient of one "
+                  "GPU / world, max |diff| / max |grad|, worst rank; tolerance 1e-9")
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sympa_b200 import distributed as sd
+
+    rank, world, local = sd.init_process_group()
+    assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    dev = torch.device("cuda", local)
+    kind, n, rows = args.kind, args.n, args.rows
+    global_pairs = args.pairs if args.pairs else GLOBAL_PAIRS
+    warmup = max(args.warmup, 3)
+    pcheck = parity_check(rank, world, dev) if world > 1 else None
+
+    res = measure(kind, n, args.metric, rows, global_pairs, args.steps, warmup, rank, world, local, dev)
+    peaks, peak_src = load_peaks()
+    fp64_peak, fp64_clocks = measure_fp64_peak(dev, local)
+    roofline = roofline_of(kind, n, res, fp64_peak, fp64_clocks, peaks, peak_src, rows)
+    par = (f"dp{world}: the batch sharded over the ranks ({res['pairs_per_gpu_per_step']} pairs per GPU and step), table "
+           "replicated, one NCCL all-reduce (average) of the table gradient per step")
     out = {
-        "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "Siegel dist pairs/s fwd+bwd", "value": res["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"distance microbench: {kind} n={n} metric={args.metric}, table 2^{rows.bit_length() - 1} rows, "
-                               f"{b} pairs/GPU/step, fwd+bwd through AverageDistortionLoss",
-                   "pairs_per_gpu_per_step": b, "rows": rows, "n": n, "kind": kind, "metric": args.metric,
-                   "l2": "table + saved unit gradients + indices exceed L2 every step (no explicit flush needed)",
-                   "parallelism": f"dp{world} pairs sharded, table replicated, one NCCL all-reduce (average) of the packed "
-                                  "table gradient inside the backward"},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(idx_h.numel() * idx_h.element_size() + gd_h.numel() * gd_h.element_size()),
-                "d2h_bytes_per_step": 8,
-                "how": "manifold.dist_from_table + AverageDistortionLoss + backward per step; every step's index pairs (int32 "
-                       "on the host, widened on the device) and graph distances (float64) are copied from pinned host memory (sympa_b200.feeder.PairFeeder: the copy of step "
-                       "k+1 overlaps the compute of step k on a side stream; the first copy is exposed), the loss is read "
-                       "back and the host waits for it every step"},
-        # our kernels per step: forward+unit-gradient kernel, then either the direct scatter (1) or the packed scatter +
-        # expansion (2) - torch's loss / fill kernels are not counted
-        "gpu_launches": (1 + (2 if (ops.backward_workspace_for(kind, n, rows, dev)[1] > 0 and 2 * b >= rows) else 1)) * args.steps,
-        "fused_step": {"pairs_per_s": world * b / (ms_fused * 1e-3), "ms_per_step": ms_fused, "launches_per_step": 1},
-        "clocks": clocks,
+        "config": {"workload": f"distance microbench (BASELINE.json configs[4]): {kind} n={n} metric={args.metric}, table "
+                               f"2^{rows.bit_length() - 1} rows, one batch of {global_pairs} random pairs per step (sharded "
+                               f"over {world} GPU(s), chunks of {res['chunk_pairs']} pairs per API call), fwd+bwd through "
+                               "AverageDistortionLoss",
+                   "global_pairs_per_step": global_pairs, "pairs_per_gpu_per_step": res["pairs_per_gpu_per_step"],
+                   "chunk_pairs": res["chunk_pairs"], "rows": rows, "n": n, "kind": kind, "metric": args.metric,
+                   "l2": "table (268 MB at n=4) + saved unit gradients + indices of a chunk exceed the 126 MB L2 many times "
+                         "over (no explicit flush needed)",
+                   "parallelism": par},
+        "e2e": res["e2e"],
+        "gpu_launches": res["gpu_launches"],
+        "gpu_launches_how": f"{res['launches_per_chunk']} kernels of libsympa_b200.so per chunk x {res['chunks_per_step']} "
+                            f"chunks x {args.steps} steps (forward + unit gradients, loss forward, loss backward, table-gradient "
+                            "scatter [+ expansion]); torch's fill / accumulate kernels and NCCL's are not counted",
+        "fused_step": res["fused_step"],
+        "clocks": res["clocks"],
         "roofline": roofline,
     }
+    if pcheck is not None:
+        out["parity_check"] = pcheck
+    if not args.no_n10:   # the other matrix size named by BASELINE.json's metric, as a record of its own
+        r10 = measure("upper", 10, "fmin", rows, N10_GLOBAL_PAIRS, max(3, min(args.steps, 5)), 3, rank, world, local, dev,
+                      fused=False)
+        out["n10"] = {"metric": "Siegel dist pairs/s fwd+bwd", "value": r10["value"], "unit": "pairs/s",
+                      "ms_per_step": r10["ms_per_step"], "steps": max(3, min(args.steps, 5)), "warmup": 3,
+                      "config": {"workload": f"distance microbench: upper n=10 metric=fmin, table 2^{rows.bit_length() - 1} rows, one "
+                                             f"batch of {N10_GLOBAL_PAIRS} random pairs per step (sharded over {world} GPU(s), "
+                                             f"chunks of {r10['chunk_pairs']}), fwd+bwd through AverageDistortionLoss",
+                                 "global_pairs_per_step": N10_GLOBAL_PAIRS, "rows": rows, "n": 10, "kind": "upper",
+                                 "metric": "fmin"},
+                      "e2e": r10["e2e"], "clocks": r10["clocks"], "gpu_launches": r10["gpu_launches"],
+                      "roofline": roofline_of("upper", 10, r10, fp64_peak, fp64_clocks, peaks, peak_src, rows)}
     if not args.no_extras:
         out["also"] = extras(args, world, rank, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,19 +546,19 @@ def run_ours(args):
 
 
 def quick_pairs_per_s(kind, n, metric, pairs, rows, dev, world, steps=5):
-    """resident fwd+bwd pairs/s of another configuration (same step shape as the main measurement)."""
+    """resident fwd+bwd pairs/s of another configuration (one chunk per rank and step)."""
     import torch.distributed as dist
-    from sympa_b200 import BoundedDomainManifold, MetricType, SymmetricPositiveDefinite, UpperHalfManifold
-    from sympa_b200 import distributed as sd
-    man = (SymmetricPositiveDefinite() if kind == "spd" else
-           {"upper": UpperHalfManifold, "bounded": BoundedDomainManifold}[kind](dims=n, metric=MetricType.from_str(metric))).to(dev)
+    from sympa_b200.losses import AverageDistortionLoss
+    man = make_manifold(kind, n, metric, dev)
+    loss_fn = AverageDistortionLoss()
     table = make_table(kind, n, rows, dev, seed=2).requires_grad_(True)
-    idx, gd = make_pairs(rows, pairs, dev, seed=300)
+    idx, gd8 = make_pairs(rows, pairs, dev, seed=300)
+    gd = gd8.double()
 
     def step():
         table.grad = None
         d = man.dist_from_table(table, idx, sync_grad=world > 1)
-        distortion_loss(gd, d).backward()
+        loss_fn.calculate_loss(gd, d).backward()
 
     for _ in range(3):
         step()
@@ -416,27 +579,57 @@ def quick_pairs_per_s(kind, n, metric, pairs, rows, dev, world, steps=5):
     return world * pairs * steps / (ms * 1e-3)
 
 
-def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, config=1):
-    """Seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept), batch 2048, RiemannianSGD.
-    config 1 (BASELINE configs[0]): grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2;
-    config 2 (BASELINE configs[1]): balanced tree branching 3 height 5 (364 nodes, 66 066 pairs), bounded / fone / n=3."""
+def dropin_pairs_per_s(dev, n=4, pairs=1 << 21, rows=1 << 20, steps=5):
+    """The literal drop-in path of the north star - the reference's model.py / losses.py unchanged around the
+    replaced manifold: two torch gathers (sympa/embeddings.py:29-34), manifold.dist(z1, z2) on MATERIALISED operands
+    (model.py:32-38), the reference's loss expression (losses.py:16-19), autograd backward with torch's dense
+    index_put gather-backward into the (N, 2, n, n) gradient."""
+    man = make_manifold("upper", n, "riem", dev)
+    table = make_table("upper", n, rows, dev, seed=3).requires_grad_(True)
+    idx, gd8 = make_pairs(rows, pairs, dev, seed=301)
+    gd = gd8.double()
+
+    def step():
+        table.grad = None
+        d = man.dist(table[idx[:, 0]], table[idx[:, 1]])
+        reference_loss(gd, d).backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return pairs * steps / (e0.elapsed_time(e1) * 1e-3)
+
+
+def _epoch_model(config, dev):
     from types import SimpleNamespace
-    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets, product_tree_grid_triplets
     from sympa_b200.model import Model
+    torch.manual_seed(0)
+    if config == 1:     # BASELINE configs[0]: grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2
+        idx, gd, nodes = grid_triplets(20, 2)
+        a = dict(manifold="upper", metric="riem", dims=2)
+    elif config == 2:   # BASELINE configs[1]: balanced tree branching 3 height 5 (364 nodes, 66 066 pairs), bounded / fone / n=3
+        idx, gd, nodes = balanced_tree_triplets(3, 5)
+        a = dict(manifold="bounded", metric="fone", dims=3)
+    else:               # BASELINE configs[2]: product tree(2,4) x grid(4x4) (496 nodes, 122 760 pairs), upper / finf / n=6
+        idx, gd, nodes = product_tree_grid_triplets(2, 4, 4, 2)
+        a = dict(manifold="upper", metric="finf", dims=6)
+    args = SimpleNamespace(num_points=nodes, scale_init=1.0, scale_coef=1.0, train_scale=False, **a)
+    return Model(args).to(dev), idx.to(dev), gd.to(dev)
+
+
+def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, config=1):
+    """Seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept), batch 2048, RiemannianSGD."""
     from sympa_b200.optim import RiemannianSGD
     from sympa_b200.runner import train_epoch
-    torch.manual_seed(0)
-    if config == 1:
-        idx, gd, nodes = grid_triplets(20, 2)
-        args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
-                               train_scale=False)
-    else:
-        idx, gd, nodes = balanced_tree_triplets(3, 5)
-        args = SimpleNamespace(manifold="bounded", metric="fone", dims=3, num_points=nodes, scale_init=1.0, scale_coef=1.0,
-                               train_scale=False)
-    model = Model(args).to(dev)
+    model, idx, gd = _epoch_model(config, dev)
     opt = RiemannianSGD(model.parameters(), lr=1e-2 * world, fused=fused)
-    idx, gd = idx.to(dev), gd.to(dev)
     train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=0, sync_stats=sync_stats)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -448,23 +641,11 @@ def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, confi
 
 def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
     """The same epochs on sympa_b200.runner.FusedEpochRunner: two launches per step (fused distortion step, fused
-    optimizer row kernel with clipping and zero_grad), the epoch replayed from a CUDA graph on one GPU, the loss
-    read back once per epoch."""
-    from types import SimpleNamespace
-    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
-    from sympa_b200.model import Model
+    optimizer row kernel with clipping and zero_grad), the epoch replayed from a CUDA graph, the loss read back
+    once per epoch."""
     from sympa_b200.runner import FusedEpochRunner
-    torch.manual_seed(0)
-    if config == 1:
-        idx, gd, nodes = grid_triplets(20, 2)
-        args = SimpleNamespace(manifold="upper", metric="riem", dims=2, num_points=nodes, scale_init=1.0, scale_coef=1.0,
-                               train_scale=False)
-    else:
-        idx, gd, nodes = balanced_tree_triplets(3, 5)
-        args = SimpleNamespace(manifold="bounded", metric="fone", dims=3, num_points=nodes, scale_init=1.0, scale_coef=1.0,
-                               train_scale=False)
-    model = Model(args).to(dev)
-    runner = FusedEpochRunner(model, 1e-2 * world, idx.to(dev), gd.to(dev), 2048, world_size=world, rank=rank)
+    model, idx, gd = _epoch_model(config, dev)
+    runner = FusedEpochRunner(model, 1e-2 * world, idx, gd, 2048, world_size=world, rank=rank)
     runner.run_epoch(0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -475,50 +656,77 @@ def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
 
 
 def extras(args, world, rank, dev):
-    """The other sizes BASELINE.json's metric names (n = 10) and its epoch-time leg, measured briefly."""
+    """Side measurements: other sizes, the literal drop-in path, BASELINE.json's epoch-time leg (configs 1-3)."""
     out = {}
     try:
-        out["upper_n10_fmin_pairs_per_s"] = quick_pairs_per_s("upper", 10, "fmin", 1 << 18, 1 << 18, dev, world)
         out["upper_n2_riem_pairs_per_s"] = quick_pairs_per_s("upper", 2, "riem", 1 << 22, 1 << 20, dev, world)
+        out["upper_n6_finf_pairs_per_s"] = quick_pairs_per_s("upper", 6, "finf", 1 << 20, 1 << 20, dev, world)
         out["spd_n10_pairs_per_s"] = quick_pairs_per_s("spd", 10, "riem", 1 << 18, 1 << 18, dev, world)
         out["bounded_n3_fone_pairs_per_s"] = quick_pairs_per_s("bounded", 3, "fone", 1 << 22, 1 << 20, dev, world)
-        sec, loss = epoch_seconds(dev, world, rank, fused=True, sync_stats=True)
-        out["train_epoch_sec_config1_grid400_upper_riem_n2_b2048"] = sec
-        out["train_epoch_final_loss"] = loss
+        if world == 1:
+            out["dropin_pairs_per_s"] = dropin_pairs_per_s(dev)
+            out["dropin_how"] = ("upper n=4, 2^21 pairs/step: table[idx] gathers + manifold.dist(z1, z2) on materialised operands "
+                                 "+ the reference's loss expression + torch's dense index_put backward (model.py:16-38, "
+                                 "losses.py:16-19 as shipped)")
+        for cfg, name in ((1, "config1_grid400_upper_riem_n2"), (2, "config2_tree_b3h5_bounded_fone_n3"),
+                          (3, "config3_product_tree2x4_grid4x4_upper_finf_n6")):
+            sec, loss = epoch_seconds(dev, world, rank, fused=True, sync_stats=True, config=cfg)
+            out[f"train_epoch_sec_{name}_b2048"] = sec
+            out[f"train_epoch_final_loss_{name}"] = loss
+            sec_g, loss_g = fused_epoch_seconds(dev, world, rank, config=cfg)
+            out[f"train_epoch_sec_{name}_fused_graph"] = sec_g
+            out[f"train_epoch_final_loss_{name}_fused_graph"] = loss_g
         sec_h, _ = epoch_seconds(dev, world, rank, fused=False, sync_stats=True)
         out["train_epoch_sec_config1_host_optimizer"] = sec_h
-        sec_n, _ = epoch_seconds(dev, world, rank, fused=True, sync_stats=False)
-        out["train_epoch_sec_config1_no_per_step_item_sync"] = sec_n
-        for cfg, key in ((1, "train_epoch_sec_config1_fused_graph"), (2, "train_epoch_sec_config2_fused_graph")):
-            sec_g, loss_g = fused_epoch_seconds(dev, world, rank, config=cfg)
-            out[key] = sec_g
-            out[key.replace("_sec_", "_final_loss_")] = loss_g
-        sec2, loss2 = epoch_seconds(dev, world, rank, fused=True, sync_stats=True, config=2)
-        out["train_epoch_sec_config2_tree_b3h5_bounded_fone_n3_b2048"] = sec2
-        out["train_epoch_config2_final_loss"] = loss2
     except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
         out["error"] = repr(e)
     return out
 
 
-def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
-    """The oracle port (the reference's own torch op sequence, oracle/siegel_oracle.py) timed on the
-    host cores: gather -> dist -> distortion loss -> autograd backward, float64."""
+# ------------------------------------------------------------------------------------------ CPU legs
+def _reference_dist_fn(kind, n, metric):
+    """manifold.dist of the UNMODIFIED reference when oracle/_ref holds a copy of its package (made by
+    oracle/make_ref.py in the build container; git-ignored, travels to the GPU box), else the oracle port.
+    Returns (callable(z1, z2) -> dist, kind_label)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if kind != "spd" and os.path.isdir(os.path.join(ref_root, "sympa")):
+        try:
+            os.environ["SYMPA_REFERENCE_ROOT"] = ref_root
+            import import_reference
+            import_reference.REFERENCE_ROOT = ref_root
+            import_reference.import_reference()
+            from sympa.manifolds import BoundedDomainManifold, UpperHalfManifold
+            from sympa.manifolds.metrics import MetricType
+            torch.set_default_dtype(torch.float64)      # what sympa/config.py:17-18 does
+            man = (UpperHalfManifold if kind == "upper" else BoundedDomainManifold)(dims=n, metric=MetricType.from_str(metric))
+            return (lambda z1, z2: man.dist(z1, z2)), "reference"
+        except Exception:  # noqa: BLE001
+            pass
     import siegel_oracle as so
+    return (lambda z1, z2: so.dist(kind, z1, z2, metric if kind != "spd" else "riem")), "port"
 
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    rows = 1 << 14
+
+def _cpu_step_fn(kind, n, metric, rows, b):
+    dist_fn, label = _reference_dist_fn(kind, n, metric)
     table = make_table(kind, n, rows, torch.device("cpu"), seed=1).requires_grad_(True)
-    b = 1 << 14
-    idx, gd = make_pairs(rows, b, torch.device("cpu"), seed=100)
+    idx, gd8 = make_pairs(rows, b, torch.device("cpu"), seed=100)
+    gd = gd8.double()
 
     def step():
         table.grad = None
-        d = so.dist(kind, table[idx[:, 0]], table[idx[:, 1]], metric if kind != "spd" else "riem")
-        distortion_loss(gd, d).backward()
+        d = dist_fn(table[idx[:, 0]], table[idx[:, 1]])      # gathers + dist, as Model.forward (model.py:16-38)
+        reference_loss(gd, d).backward()                      # losses.py:16-19 + autograd, dense index_put backward
+    return step, label
 
+
+def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
+    """The reference's own CPU implementation of the path timed on the host cores: gather -> dist -> distortion loss
+    -> autograd backward, float64, on a bounded sample of the workload."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rows, b = 1 << 14, 1 << 14
+    step, label = _cpu_step_fn(kind, n, metric, rows, b)
     step()
     t0 = time.perf_counter()
     reps = 0
@@ -528,8 +736,9 @@ def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
         el = time.perf_counter() - t0
         if el > budget_s or reps >= 50:
             break
-    return {"value": b * reps / el, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"{reps} x {b} pairs of the same workload ({kind} n={n}), torch CPU float64, {el:.1f} s"}
+    return {"value": b * reps / el, "unit": "pairs/s", "cores": threads, "kind": label,
+            "sample": f"{reps} steps x {b} pairs of the same workload ({kind} n={n} metric={metric}, table 2^14 rows), "
+                      f"torch CPU float64, {el:.1f} s"}
 
 
 def run_reference(args):
@@ -538,36 +747,27 @@ def run_reference(args):
         return
     kind, n = args.kind, args.n
     threads = os.cpu_count() or 1
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import siegel_oracle as so
     torch.set_num_threads(threads)
-    rows = 1 << 14
-    b = 1 << 13
-    table = make_table(kind, n, rows, torch.device("cpu"), seed=1).requires_grad_(True)
-    idx, gd = make_pairs(rows, b, torch.device("cpu"), seed=100)
-
-    def step():
-        table.grad = None
-        d = so.dist(kind, table[idx[:, 0]], table[idx[:, 1]], args.metric if kind != "spd" else "riem")
-        distortion_loss(gd, d).backward()
-
-    for _ in range(max(1, min(args.warmup, 3))):
+    rows, b = 1 << 14, 1 << 13
+    step, label = _cpu_step_fn(kind, n, args.metric, rows, b)
+    warmup = max(1, args.warmup)
+    for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     el = time.perf_counter() - t0
     value = b * args.steps / el
-    cfg_b = args.pairs if args.pairs else default_pairs(n)
+    sample = (f"each step = {b} pairs (a bounded sample of the 2^26-pair batch), table 2^14 rows, gather -> manifold.dist -> "
+              f"losses.py expression -> autograd backward, torch CPU float64, {threads} threads")
     out = {
         "impl": "reference", "metric": "Siegel dist pairs/s fwd+bwd", "value": value, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"distance microbench: {kind} n={n} metric={args.metric}, table 2^{args.rows.bit_length() - 1} rows, "
-                               f"{cfg_b} pairs/GPU/step, fwd+bwd through AverageDistortionLoss",
-                   "n": n, "kind": kind, "metric": args.metric},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"each step = {b} pairs of the workload (bounded sample), table 2^14 rows, torch CPU float64"},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"distance microbench (BASELINE.json configs[4]): {kind} n={n} metric={args.metric}; this CPU arm "
+                               f"runs a bounded sample per step: {b} pairs on a table of {rows} rows",
+                   "pairs_per_step": b, "rows": rows, "n": n, "kind": kind, "metric": args.metric},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": label, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -584,9 +784,10 @@ def main():
     ap.add_argument("--n", type=int, default=4)
     ap.add_argument("--metric", default="riem")
     ap.add_argument("--rows", type=int, default=1 << 20)
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default by n)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs of the whole batch per step (default 2^26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the n=10 / epoch-time side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other sizes, epoch times)")
+    ap.add_argument("--no-n10", action="store_true", help="skip the n = 10 record")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

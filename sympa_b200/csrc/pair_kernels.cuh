@@ -100,6 +100,10 @@ int grid_for(int64_t work_items, int threads, int waves_cap);
 #ifndef SY_PAIR_THREADS
 #define SY_PAIR_THREADS 128
 #endif
+// waves of resident CTAs in the grid of the pair kernels (launch_one)
+#ifndef SY_PAIR_WAVES
+#define SY_PAIR_WAVES 8
+#endif
 constexpr int kThreads = SY_PAIR_THREADS;
 // Re-align the warps of a CTA at the start of every pair and after its Jacobi sweeps (two
 // __syncthreads per ~10k instructions): the fully unrolled body is several times larger than the
@@ -246,12 +250,12 @@ struct StageCfg {
                               (KIND != kSpd);
   static constexpr int RC = PER / 2;                           // 16-byte chunks per point
   static constexpr int IN_STRIDE = 2 * RC + 1;                 // chunks per pair slot (two points + pad)
-  // point slot on the way out: the fused step (mode 2) stages full points (RC chunks) for its atomics,
-  // the forward+save kernel (mode 1) packed saved state (SRC chunks); plus one pad chunk (carries the
-  // destination row in the fused step), rounded up to an odd number of chunks
+  // on the way out: the forward+save kernel (mode 1) stages the packed saved state of both operands as two
+  // CONTIGUOUS blocks [operand][lane][SRC chunks] - exactly the bytes of 32 consecutive pairs in HBM, so one bulk
+  // store per operand and warp moves them; the fused step (mode 2) stages one full point per lane at a time (RC
+  // chunks) plus a pad chunk that carries the destination row, at an odd chunk stride, for its row-contiguous atomics
   static constexpr int SRC = state_doubles(KIND, N) / 2;
-  __host__ __device__ static constexpr int out_rc(int mode) { return mode == 2 ? RC : SRC; }
-  __host__ __device__ static constexpr int out_stride(int mode) { return (out_rc(mode) % 2 == 0) ? out_rc(mode) + 1 : out_rc(mode) + 2; }
+  __host__ __device__ static constexpr int out_stride(int mode) { return mode == 2 ? ((RC % 2 == 0) ? RC + 1 : RC + 2) : 2 * SRC; }
   static constexpr int IN_BYTES = 32 * IN_STRIDE * 16;
   static constexpr int IDX_BYTES = 2 * 32 * 16;                // two generations of 32 index pairs
   // per-warp layout: [rows in][indices][gradients out - not in the forward-only kernel]
@@ -260,11 +264,31 @@ struct StageCfg {
   }
 };
 
+// (no "memory" clobber: the statement neither reads nor writes anything the compiler knows about before the
+// cp.async.wait_all that follows it, and with the clobber every copy was a barrier for the shared-memory load
+// of the NEXT copy's row index - 32 dependent LDS -> LDGSTS round trips per warp and pair, 6 % of the kernel
+// time in ncu.  Ordering against the slot's previous readers is the __syncwarp() before stage_rows.)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// TMA one-dimensional bulk store shared -> global (16-byte aligned addresses, bytes a multiple of 16), tracked
+// by the issuing thread's bulk async-group.  A bulk copy is a warp-uniform instruction (UBLKCP): issued per lane
+// the compiler serialises it in a loop over the lanes (measured: 1100 extra instructions per warp and pair),
+// so it is used where ONE copy moves a warp's worth of data - the saved unit gradients of 32 consecutive
+// pairs are contiguous in HBM - and not for the gather of 64 scattered rows, which stays with cp.async.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders this thread's generic-proxy writes to shared memory before later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // index pairs of the warp's 32 pairs starting at pair w0 -> idxb[0..31] (asynchronous).  Pairs past the
 // end are clamped to the last one: every warp of a CTA that still has work computes on valid data.
@@ -272,7 +296,9 @@ __device__ __forceinline__ void stage_indices(const PairArgs& a, int64_t w0, lon
   if (a.idx == nullptr) return;
   int64_t p = w0 + lane;
   p = p < a.num_pairs ? p : a.num_pairs - 1;
+  asm volatile("" ::: "memory");
   cp_async16(idxb + lane, reinterpret_cast<const longlong2*>(a.idx) + p);
+  asm volatile("" ::: "memory");
 }
 
 // Owner lanes check the (landed) index pairs of a generation once, replace rejected ones by (0, 0) in
@@ -293,6 +319,9 @@ template <int N, int KIND>
 __device__ __forceinline__ void stage_rows(const PairArgs& a, int64_t w0, const longlong2* idxb, unsigned char* in,
                                            int lane) {
   using S = StageCfg<N, KIND>;
+  // compiler fence: the copies below carry no "memory" clobber (see cp_async16), so without it the loads that
+  // moved the CURRENT pairs' operands out of the slots could be scheduled after the copies that refill them
+  asm volatile("" ::: "memory");
   // flat chunk f = it * 32 + lane among the warp's 32 pairs: pair j = f / (2 RC), then the point
   // (side 0 / 1) and the chunk c within the point
   if (a.idx != nullptr) {
@@ -319,6 +348,7 @@ __device__ __forceinline__ void stage_rows(const PairArgs& a, int64_t w0, const 
       cp_async16(in + (j * S::IN_STRIDE + rem) * 16, (side ? a.z2 : a.z1) + p * S::PER + 2 * c);
     }
   }
+  asm volatile("" ::: "memory");
 }
 
 // one symmetric n x n block from shared memory -> packed lower triangle, symmetrised
@@ -338,22 +368,6 @@ __device__ __forceinline__ void load_packed_smem(const double* p, double* s) {
     for (int i = 0; i < N * N; ++i) buf[i] = p[i];
   }
   reg::pack_sym<N>(buf, s);
-}
-
-// the warp's 32 staged points of saved state (slot stride out_stride(1) chunks) -> 32 consecutive points in HBM
-template <int N, int KIND>
-__device__ __forceinline__ void flush_points(const unsigned char* out, double* __restrict__ dst, int64_t w0,
-                                             int64_t num_pairs, int lane) {
-  using S = StageCfg<N, KIND>;
-  constexpr int RC = S::out_rc(1), STRIDE = S::out_stride(1);
-  double2* d2 = reinterpret_cast<double2*>(dst + w0 * (2 * RC));
-#pragma unroll
-  for (int it = 0; it < RC; ++it) {
-    const int f = it * 32 + lane;
-    const int j = f / RC;
-    const int c = f - j * RC;
-    if (w0 + j < num_pairs) __stcs(d2 + f, *reinterpret_cast<const double2*>(out + (j * STRIDE + c) * 16));
-  }
 }
 
 // the warp's 32 staged (already scaled) point gradients -> scatter-add into the table gradient,
@@ -421,8 +435,12 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
       __syncwarp();
       bad_next = validate_indices(a, st_idx, lane);
       stage_rows<N, KIND>(a, b0 + wofs, st_idx, st_in, lane);
+      cp_async_wait_all();   // the first rows: exposed once per CTA
     }
   }
+#ifdef SY_DEPHASE_NS
+  if (blockIdx.x & 1) __nanosleep(SY_DEPHASE_NS);   // experiment: start the odd CTAs half an iteration late
+#endif
   int gen = 0;  // generation (parity) of the index buffer holding the current pairs
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.num_pairs; base += stride, gen ^= 1) {
     if (SY_BLOCK_SYNC && REG && N >= SY_SYNC_MIN_N) __syncthreads();
@@ -433,7 +451,9 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
     const double* p2;
     int64_t i1 = 0, i2 = 0;
     if (STAGE) {
-      cp_async_wait_all();   // rows of this iteration (issued one iteration ago), indices of the next
+      // (the rows of this iteration and the indices of the next were waited for at the END of the previous
+      // iteration, before its bulk stores were issued: LDGSTS groups and bulk groups are tracked by the same
+      // dependency barrier, and a wait placed here also sat out the stores just issued - 0.6 us per iteration)
       __syncwarp();
       if (a.idx != nullptr) {
         if (MODE == kModeStep) {  // only the fused step scatters by row
@@ -545,10 +565,13 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
 #pragma unroll
       for (int k = 0; k < N; ++k) a.vvd_out[p * N + k] = vs[k];
     }
+    if (STAGE) cp_async_wait_all();   // next iteration's rows and indices (issued at the top of this one): long done
     if (STAGE && MODE == kModeFwdSave) {
-      // unit gradients -> own slot -> contiguous segments of the saved state (zeros for a pair whose
-      // indices were rejected; the tail is cut off in flush_points)
-      double* os = reinterpret_cast<double*>(st_out + lane * (S::out_stride(1) * 16));
+      // unit gradients -> the warp's two contiguous blocks -> one bulk store per operand into the saved state
+      // (zeros for a pair whose indices were rejected; the tail is cut off by the byte count)
+      constexpr int PS = state_doubles(KIND, N);
+      double* o1 = reinterpret_cast<double*>(st_out) + lane * PS;
+      double* o2 = o1 + 32 * PS;
       if (!active) {
 #pragma unroll
         for (int i = 0; i < T; ++i) {
@@ -560,13 +583,20 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
           }
         }
       }
-      store_state<N, KIND != kSpd>(os, g1r, g1i);
+      if (lane == 0) bulk_wait_read();   // the stores of the previous iteration have read the blocks (long ago)
       __syncwarp();
-      flush_points<N, KIND>(st_out, a.gz1, base + wofs, a.num_pairs, lane);
+      store_state<N, KIND != kSpd>(o1, g1r, g1i);
+      store_state<N, KIND != kSpd>(o2, g2r, g2i);
+      fence_async_smem();
       __syncwarp();
-      store_state<N, KIND != kSpd>(os, g2r, g2i);
-      __syncwarp();
-      flush_points<N, KIND>(st_out, a.gz2, base + wofs, a.num_pairs, lane);
+      const int64_t w0 = base + wofs;
+      const int64_t left = a.num_pairs - w0;   // pairs of this warp that exist (<= 0: a warp of the tail)
+      if (lane == 0 && left > 0) {
+        const unsigned bytes = (unsigned)((left < 32 ? left : 32) * (PS * 8));
+        bulk_s2g(a.gz1 + w0 * PS, st_out, bytes);
+        bulk_s2g(a.gz2 + w0 * PS, reinterpret_cast<double*>(st_out) + 32 * PS, bytes);
+        bulk_commit();
+      }
     } else if (active && MODE == kModeFwdSave) {
       if (REG) {  // packed saved state (state_is_packed)
         constexpr int PS = state_doubles(KIND, N);
@@ -636,6 +666,7 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
     }
   }
   if (STAGE) cp_async_wait_all();
+  if (STAGE && MODE == kModeFwdSave && lane == 0) bulk_wait_all();
   if (MODE == kModeStep) {
     loss_acc = warp_sum(loss_acc);
     gscale_acc = warp_sum(gscale_acc);
@@ -656,20 +687,31 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
 
 template <int N, int KIND, int MODE>
 static int launch_one(const PairArgs& a, cudaStream_t s) {
-  // grid-stride launch sized in whole waves of the SM count
-  const int grid = grid_for(a.num_pairs, kThreads, 16);
   int smem = 0;
-  if (StageCfg<N, KIND>::kOn) {
-    smem = (kThreads / 32) * StageCfg<N, KIND>::warp_bytes(MODE);
-    static bool configured[64] = {};  // per instantiation and device (the attribute is per function per device)
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      if (cudaFuncSetAttribute(pair_kernel<N, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return check_launch();
-      if (dev >= 0 && dev < 64) configured[dev] = true;
+  if (StageCfg<N, KIND>::kOn) smem = (kThreads / 32) * StageCfg<N, KIND>::warp_bytes(MODE);
+  static bool configured[64] = {};  // per instantiation and device (the attribute is per function per device)
+  static int resident[64] = {};     // CTAs of this instantiation that fit on one SM
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int occ = 0;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (smem > 0 &&
+        cudaFuncSetAttribute(pair_kernel<N, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return check_launch();
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<N, KIND, MODE>, kThreads, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+    if (dev >= 0 && dev < 64) {
+      configured[dev] = true;
+      resident[dev] = occ;
     }
+  } else {
+    occ = resident[dev];
   }
+  // Grid-stride launch of SY_PAIR_WAVES x (the CTAs resident at once).  Measured at n = 4, 2^23 pairs: 1 wave
+  // (fully persistent) 3.67 ms, 2 waves 3.58 ms, 8 waves 3.44 ms - with a single wave the two CTAs of an SM run
+  // in lockstep, both in their gather / store phases at the same time, and the FP64 pipe idles; CTAs that
+  // retire and start at different times de-phase the SM.
+  const int grid = grid_for(a.num_pairs, kThreads, SY_PAIR_WAVES * occ);
   pair_kernel<N, KIND, MODE><<<grid, kThreads, smem, s>>>(a);
   return check_launch();
 }

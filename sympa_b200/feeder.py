@@ -5,7 +5,9 @@ not fit (5e11 pairs, sampled) or that arrive from a hos
 batch (index pairs int64 (b, 2), graph distances float64 (b,)) has to cross PCIe every step.
 PairFeeder double-buffers that copy on a side stream: while batch k computes, batch k + 1 is on the
 wire, so a step costs max(copy, compute) instead of their sum.  Host tensors must be pinned.  The index
-pairs may be int32 on the host (node ids fit; half the bytes): they are widened to int64 on the device.
+pairs may be int32 on the host (node ids fit; half the bytes) and the graph distances small integers (uint8 /
+int16: shortest-path lengths of an unweighted graph, preprocess.py:118-126): both are widened on the device -
+9 bytes per pair on the wire instead of 24.
 """
 import torch
 
@@ -27,12 +29,15 @@ class PairFeeder:
         assert self._in_flight < self.depth, "PairFeeder: all slots in flight (call next()/done() first)"
         assert idx_h.is_pinned() and gd_h.is_pinned(), "PairFeeder needs pinned host memory"
         s = self._head
-        buf = self._bufs[s]
         narrow = idx_h.dtype == torch.int32     # node ids as int32 on the host: 8 instead of 16 bytes per pair on the wire
-        if buf is None or buf[0].shape != idx_h.shape or buf[1].shape != gd_h.shape or (buf[2] is None) == narrow:
+        small = gd_h.dtype != torch.float64     # graph distances as small integers (uint8 / int16) on the host
+        buf = self._bufs[s]
+        if (buf is None or buf[0].shape != idx_h.shape or buf[1].shape != gd_h.shape or (buf[2] is None) == narrow
+                or (buf[3] is None) == small or (small and buf[3].dtype != gd_h.dtype)):
             buf = (torch.empty(idx_h.shape, dtype=torch.int64, device=self.device),
-                   torch.empty(gd_h.shape, dtype=gd_h.dtype, device=self.device),
-                   torch.empty(idx_h.shape, dtype=torch.int32, device=self.device) if narrow else None)
+                   torch.empty(gd_h.shape, dtype=torch.float64, device=self.device),
+                   torch.empty(idx_h.shape, dtype=torch.int32, device=self.device) if narrow else None,
+                   torch.empty(gd_h.shape, dtype=gd_h.dtype, device=self.device) if small else None)
             self._bufs[s] = buf
         with torch.cuda.stream(self.copy_stream):
             if self._consumed[s] is not None:
@@ -42,7 +47,11 @@ class PairFeeder:
                 buf[0].copy_(buf[2])                             # widened on the device (the kernels take int64 indices)
             else:
                 buf[0].copy_(idx_h, non_blocking=True)
-            buf[1].copy_(gd_h, non_blocking=True)
+            if small:
+                buf[3].copy_(gd_h, non_blocking=True)
+                buf[1].copy_(buf[3])                             # widened to float64 on the device
+            else:
+                buf[1].copy_(gd_h, non_blocking=True)
             self._ready[s].record(self.copy_stream)
         self._head = (s + 1) % self.depth
         self._in_flight += 1

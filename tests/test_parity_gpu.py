@@ -17,8 +17,11 @@ RTOL, ATOL = 1e-9, 1e-12
 
 @pytest.fixture(scope="module")
 def sb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
     import sympa_b200
-    assert torch.cuda.is_available()
+    from sympa_b200 import _lib
+    _lib.load()      # a missing libsympa_b200.so is an error on a GPU box, never a silent fallback
     return sympa_b200
 
 
@@ -59,7 +62,13 @@ def test_manifold_dist_matches_reference_golden(sb, path):
 
 @pytest.mark.parametrize("kind,n,metric", [("upper", 2, "riem"), ("upper", 4, "fmin"), ("bounded", 3, "fone"),
                                            ("upper", 6, "finf"), ("bounded", 5, "wsum"), ("upper", 10, "fmin"),
-                                           ("spd", 3, "riem"), ("spd", 4, "riem"), ("spd", 10, "riem")])
+                                           ("upper", 1, "riem"), ("bounded", 1, "fone"), ("upper", 3, "wsum"), ("upper", 5, "fone"),
+                                           ("upper", 7, "riem"), ("upper", 8, "fmin"), ("upper", 9, "wsum"),
+                                           ("bounded", 2, "riem"), ("bounded", 4, "fmin"), ("bounded", 6, "finf"),
+                                           ("bounded", 7, "fone"), ("bounded", 8, "riem"), ("bounded", 9, "fmin"),
+                                           ("bounded", 10, "wsum"),
+                                           ("spd", 1, "riem"), ("spd", 3, "riem"), ("spd", 4, "riem"), ("spd", 7, "riem"),
+                                           ("spd", 10, "riem")])
 def test_table_path_and_fused_step_match_oracle(sb, kind, n, metric):
     """fused gather + scatter-add backward, and the one-launch distortion step, against the oracle
     run the way the reference runs it: gather -> dist -> AverageDistortionLoss -> autograd."""
@@ -283,25 +292,33 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
 
 
 
-@pytest.mark.parametrize("kind,metric,n", [("upper", "riem", 2), ("bounded", "fone", 3)])
-def test_train_epoch_matches_oracle_loop(sb, kind, metric, n):
+@pytest.mark.parametrize("kind,metric,n,graph", [("upper", "riem", 2, "grid5"), ("bounded", "fone", 3, "grid5"),
+                                                 ("upper", "riem", 2, "config1"), ("bounded", "fone", 3, "config2")])
+def test_train_epoch_matches_oracle_loop(sb, kind, metric, n, graph):
     """One epoch of the training loop (runner.py:90-122: forward, distortion loss, backward, clip,
-    RiemannianSGD) on a small grid graph against the same loop driven by the oracle on the CPU."""
+    RiemannianSGD) against the same loop driven by the oracle on the CPU: on a small grid graph, and at the
+    full size of BASELINE.json configs[0] (grid 20x20: 400 nodes, 79 800 pairs, upper / riem / n = 2, batch 2048)
+    and configs[1] (balanced tree 3/5: 364 nodes, 66 066 pairs, bounded / fone / n = 3, batch 2048)."""
     from types import SimpleNamespace
     from torch.nn.utils import clip_grad_norm_
-    from sympa_b200.graphs import grid_triplets
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
     from sympa_b200.model import Model
     from sympa_b200.optim import RiemannianSGD
     from sympa_b200.runner import train_epoch
 
     torch.manual_seed(0)
-    idx, gd, nodes = grid_triplets(5, 2)
+    if graph == "grid5":
+        (idx, gd, nodes), bs = grid_triplets(5, 2), 64
+    elif graph == "config1":
+        (idx, gd, nodes), bs = grid_triplets(20, 2), 2048
+    else:
+        (idx, gd, nodes), bs = balanced_tree_triplets(3, 5), 2048
     args = SimpleNamespace(manifold=kind, metric=metric, dims=n, num_points=nodes, scale_init=1.0, scale_coef=1.0,
                            train_scale=False)
     model = Model(args)
     table0 = model.embeddings.embeds.detach().clone()
     model = model.cuda()
-    lr, bs = 1e-2, 64
+    lr = 1e-2
     opt = RiemannianSGD(model.parameters(), lr=lr)
     mean_loss = train_epoch(model, opt, idx.cuda(), gd.cuda(), bs, max_grad_norm=50.0, shuffle=False)
 
