@@ -122,17 +122,17 @@ class ClockSampler:
 
 
 def measure_fp64_peak(dev, local):
-    """attainable FP64 FMA rate of this GPU in TFLOP/s (sympa_probe_fp64: pure DFMA chains, best of 6, CUDA events),
+    """attainable FP64 FMA rate of this GPU in TFLOP/s (sympa_probe_fp64: pure DFMA chains, best of 20 runs of ~35 ms, CUDA events),
     with the SM clock sampled while the probe runs"""
     from sympa_b200 import _lib
     lib = _lib.load()
     out = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    iters = 1 << 16
+    iters = 1 << 18
     best = 0.0
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(12):
+    for _ in range(20):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         flops = lib.sympa_probe_fp64(iters, out.data_ptr(), stream)
@@ -487,6 +487,9 @@ def run_ours(args):
     rank, world, local = sd.init_process_group()
     assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
     dev = torch.device("cuda", local)
+    if os.environ.get("SYMPA_SCATTER_PASS_MB"):     # tuning experiments only
+        from sympa_b200 import _lib
+        _lib.check(_lib.load().sympa_set_option(_lib.OPT_SCATTER_PASS_MB, int(os.environ["SYMPA_SCATTER_PASS_MB"])))
     kind, n, rows = args.kind, args.n, args.rows
     global_pairs = args.pairs if args.pairs else GLOBAL_PAIRS
     warmup = max(args.warmup, 3)

@@ -30,8 +30,11 @@ extern "C" {
 /* 3: v2 plus additive entry points (sympa_dist_matrix, sympa_dist_backward_table, sympa_table_grad_scatter /
  *    _expand, sympa_rsgd_step_ex, sympa_distortion_loss_forward / _backward) and the bounded domain in
  *    sympa_rsgd_step; the saved state of the register-kernel sizes became packed (its size still comes from
- *    sympa_workspace_bytes, its layout was never part of the interface). */
-#define SYMPA_ABI_VERSION 3
+ *    sympa_workspace_bytes, its layout was never part of the interface).
+ * 4: the saved state is packed for EVERY matrix size (so sympa_backward_workspace_bytes is non-zero and
+ *    sympa_table_grad_scatter / _expand work for all of them); the packed scatter runs in L2-sized passes
+ *    (SYMPA_OPT_SCATTER_PASS_MB); sympa_rsgd_step takes the bounded-domain gradient unsymmetrised. */
+#define SYMPA_ABI_VERSION 4
 
 /* manifold kinds: sympa/embeddings.py:144-149 ("upper", "bounded") and :142 ("spd") */
 enum { SYMPA_KIND_UPPER = 0, SYMPA_KIND_BOUNDED = 1, SYMPA_KIND_SPD = 2 };
@@ -93,6 +96,10 @@ int sympa_rsgd_step_ex(int kind, int n, int64_t num_rows, double* table, double*
  * sizes run as ONE cooperative kernel; 1 = three kernels through `scratch` (sympa_scratch_bytes then
  * reports a non-zero size).  Results are bit-identical either way. */
 #define SYMPA_OPT_SPLIT_PATH 1
+/* SYMPA_OPT_SCATTER_PASS_MB: megabytes of packed gradient table one pass of the table-gradient scatter covers
+ * (default: unlimited = one pass; passes over L2-sized row ranges measured slower on the B200, see
+ * sympa_b200.cu - kept for experiments). */
+#define SYMPA_OPT_SCATTER_PASS_MB 2
 int sympa_set_option(int option, int value);
 
 /* Diagnostic: launches a pure FP64 FMA kernel (8 independent chains per thread, 8 CTAs of 256 threads
@@ -159,7 +166,7 @@ int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs,
  *                              also dL/dw of the wsum metric when grad_wsum_w is given
  *   [ncclAllReduce over workspace, sympa_backward_workspace_bytes(kind, n, num_rows) bytes of doubles]
  *   sympa_table_grad_expand    grad_table <- (or +=) the dense symmetric rows
- * SYMPA_ERR_UNSUPPORTED for the configurations whose saved state is not packed (workspace size 0). */
+ * (Every configuration has a packed workspace since ABI 4.) */
 int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs,
                              const double* grad_dist, const double* saved_state,
                              int64_t num_rows, const int64_t* idx,
@@ -167,6 +174,14 @@ int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs,
                              double* workspace, int64_t workspace_bytes, void* stream);
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table,
                             int overwrite, void* stream);
+/* The scatter half restricted to the destination rows [row_begin, row_end): zeroes that range of the packed
+ * workspace and scatter-adds the batch's contributions to it (dL/dw of the wsum metric is NOT computed here:
+ * use sympa_dist_backward with only grad_wsum_w).  Lets a data-parallel caller pipeline the collective: scatter
+ * range k, start the all-reduce of range k on a side stream, scatter range k + 1 meanwhile - the all-reduce of
+ * DDP's dense table gradient (train.py:59) disappears behind the scatter.  num_pairs == 0 only zeroes. */
+int sympa_table_grad_scatter_rows(int kind, int n, int64_t num_pairs, const double* grad_dist, const double* saved_state,
+                                  int64_t num_rows, const int64_t* idx, int64_t row_begin, int64_t row_end,
+                                  double* workspace, int64_t workspace_bytes, void* stream);
 
 /* Bounded domain by rows.  BoundedDomainManifold.dist (bounded_domain.py:27-39) maps both operands to the upper
  * half space with the inverse Cayley transform and calls the upper-half dist.  The transform acts on points,

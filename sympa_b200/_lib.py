@@ -10,6 +10,7 @@ KIND = {"upper": 0, "bounded": 1, "spd": 2}
 METRIC = {"riem": 0, "fone": 1, "finf": 2, "fmin": 3, "wsum": 4}
 MAX_N = 10
 OPT_SPLIT_PATH = 1
+OPT_SCATTER_PASS_MB = 2
 
 STATUS_BITS = {
     1: "a point is outside the manifold (Cholesky pivot <= 0)",
@@ -37,6 +38,7 @@ EXPORTS = (
     "sympa_dist_backward_table",
     "sympa_table_grad_scatter",
     "sympa_table_grad_expand",
+    "sympa_table_grad_scatter_rows",
     "sympa_distortion_loss_forward",
     "sympa_distortion_loss_backward",
     "sympa_bounded_rows_to_upper",
@@ -90,6 +92,8 @@ def load():
     lib.sympa_dist_backward_table.argtypes = [I, I, I, L, P, P, P, L, P, P, P, P, P, L, I, P]
     lib.sympa_table_grad_scatter.restype = I
     lib.sympa_table_grad_scatter.argtypes = [I, I, I, L, P, P, L, P, P, P, P, P, L, P]
+    lib.sympa_table_grad_scatter_rows.restype = I
+    lib.sympa_table_grad_scatter_rows.argtypes = [I, I, L, P, P, L, P, L, L, P, L, P]
     lib.sympa_table_grad_expand.restype = I
     lib.sympa_table_grad_expand.argtypes = [I, I, L, P, P, I, P]
     lib.sympa_distortion_loss_forward.restype = I

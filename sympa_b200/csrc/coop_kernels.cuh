@@ -159,9 +159,11 @@ __device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* 
   double scale = 1.0;
   double* o1;
   double* o2;
+  constexpr int TRI = N * (N + 1) / 2;                    // packed lower triangle of one block
+  constexpr int PS = (KIND == kSpd ? 1 : 2) * TRI;        // saved state of one point (state_doubles)
   if (MODE == kModeFwdSave) {
-    o1 = a.gz1 + p * PER;
-    o2 = a.gz2 + p * PER;
+    o1 = a.gz1 + p * PS;
+    o2 = a.gz2 + p * PS;
   } else {  // fused distortion step: L_p = |(s d / g)^2 - 1|  (losses.py:16-19, model.py:30)
     const double gd = __ldg(a.graph_dist + p);
     const double r = a.scale * dist / gd;
@@ -178,11 +180,13 @@ __device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* 
   }
   for (int e = g; e < NN; e += G) {
     const int i = e / N, j = e - i * N, s = i * LD + j, t = j * LD + i;
+    if (MODE == kModeFwdSave && j > i) continue;          // the saved state keeps the lower triangle only
+    const int pk = i * (i + 1) / 2 + j;
     const double v1 = scale * s1 * 0.5 * (r1[s] + r1[t]);
     const double v2 = scale * 0.5 * (r2[s] + r2[t]);
     if (MODE == kModeFwdSave) {
-      o1[e] = v1;
-      o2[e] = v2;
+      o1[pk] = v1;
+      o2[pk] = v2;
     } else {
       atomicAdd(o1 + e, v1);
       atomicAdd(o2 + e, v2);
@@ -191,8 +195,8 @@ __device__ __forceinline__ void emit_gradients(const PairArgs& a, const double* 
       const double w1 = scale * 0.5 * (m1[s] + m1[t]);
       const double w2 = scale * 0.5 * (m2[s] + m2[t]);
       if (MODE == kModeFwdSave) {
-        o1[NN + e] = w1;
-        o2[NN + e] = w2;
+        o1[TRI + pk] = w1;
+        o2[TRI + pk] = w2;
       } else {
         atomicAdd(o1 + NN + e, w1);
         atomicAdd(o2 + NN + e, w2);

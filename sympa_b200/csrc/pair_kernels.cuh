@@ -598,20 +598,9 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
         bulk_commit();
       }
     } else if (active && MODE == kModeFwdSave) {
-      if (REG) {  // packed saved state (state_is_packed)
-        constexpr int PS = state_doubles(KIND, N);
-        store_state<N, KIND != kSpd>(a.gz1 + p * PS, g1r, g1i);
-        store_state<N, KIND != kSpd>(a.gz2 + p * PS, g2r, g2i);
-      } else {
-        double* o1 = a.gz1 + p * PER;
-        double* o2 = a.gz2 + p * PER;
-        store_full<N, REG>(o1, g1r);
-        store_full<N, REG>(o2, g2r);
-        if (KIND != kSpd) {
-          store_full<N, REG>(o1 + N * N, g1i);
-          store_full<N, REG>(o2 + N * N, g2i);
-        }
-      }
+      constexpr int PS = state_doubles(KIND, N);   // packed saved state
+      store_state<N, KIND != kSpd>(a.gz1 + p * PS, g1r, g1i);
+      store_state<N, KIND != kSpd>(a.gz2 + p * PS, g2r, g2i);
     }
     if (active && MODE == kModeStep) {
       // L_p = |(s d / g)^2 - 1|   (sympa/losses.py:16-19 with the scale of sympa/model.py:30)

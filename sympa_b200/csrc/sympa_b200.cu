@@ -115,7 +115,14 @@ __global__ void __launch_bounds__(256) scatter_kernel_packed(int64_t total, int 
 // so fewer and smaller DRAM read-modify-writes and a better L2 hit rate for the random rows - with fully
 // coalesced reads of the packed saved state; expand_table_kernel then writes (or adds) the dense
 // symmetric rows once.
+// Destination rows [row_lo, row_hi) only: the host runs the kernel in PASSES over row ranges small enough for
+// the range's packed gradient rows to stay resident in L2 (the whole 168 MB table of 2^20 rows at n = 4 does
+// not fit, and round 1 measured 852 B of DRAM traffic per pair - read-modify-writes of rows that had been
+// evicted - against 340 B when the accumulation happens in L2 and every row is written back once).  A pass
+// reads the saved state of an operand only when its row is in range, so the state is still read once overall;
+// the 24 bytes of indices + upstream gradient per pair are re-read by every pass.
 __global__ void __launch_bounds__(256) scatter_packed_table_kernel(int64_t total, int per_s, int64_t num_rows,
+                                                                   int64_t row_lo, int64_t row_hi,
                                                                    const double* __restrict__ gd,
                                                                    const int64_t* __restrict__ idx,
                                                                    const double* __restrict__ u1,
@@ -124,11 +131,13 @@ __global__ void __launch_bounds__(256) scatter_packed_table_kernel(int64_t total
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t p = e / per_s;
     const int c = (int)(e - p * per_s);
-    const double g = __ldg(gd + p);
     const int64_t i1 = __ldg(idx + 2 * p), i2 = __ldg(idx + 2 * p + 1);
     if (i1 < 0 || i1 >= num_rows || i2 < 0 || i2 >= num_rows) continue;
-    atomicAdd(ws + i1 * per_s + c, g * __ldg(u1 + e));
-    atomicAdd(ws + i2 * per_s + c, g * __ldg(u2 + e));
+    const bool in1 = i1 >= row_lo && i1 < row_hi, in2 = i2 >= row_lo && i2 < row_hi;
+    if (!in1 && !in2) continue;
+    const double g = __ldg(gd + p);
+    if (in1) atomicAdd(ws + i1 * per_s + c, g * __ldg(u1 + e));
+    if (in2) atomicAdd(ws + i2 * per_s + c, g * __ldg(u2 + e));
   }
 }
 
@@ -342,6 +351,40 @@ static bool valid_common(int kind, int n, int metric, int64_t num_pairs) {
 
 static int point_doubles(int kind, int n) { return (kind == SYMPA_KIND_SPD ? 1 : 2) * n * n; }
 
+// bytes of packed gradient table one scatter pass may cover (SYMPA_OPT_SCATTER_PASS_MB).  Default: one pass.
+// Passes over L2-sized row ranges were built to turn the DRAM read-modify-writes of the 168 MB packed table
+// (n = 4, 2^20 rows: 852 B of traffic per pair) into L2 hits, and measured SLOWER on the B200 (2^23 pairs:
+// 1 pass 1.52 ms, 2 passes of 84 MB 1.81 ms, 5 passes of 34 MB 2.51 ms, 9 passes 3.99 ms): every pass walks
+// all (pair, element) work items again to find the ones in range, and that walk costs more than the traffic
+// it saves.  The option stays for experiments and for sympa_table_grad_scatter_rows' range logic.
+static int64_t g_scatter_pass_bytes = 1ll << 46;
+
+// scatter-add of a batch into the rows [row_begin, row_end) of the packed gradient table, in L2-sized passes
+static int launch_packed_scatter(int64_t num_pairs, int per_s, int64_t num_rows, const double* grad_dist, const int64_t* idx,
+                                 const double* u1, const double* u2, double* workspace, cudaStream_t s,
+                                 int64_t row_begin = 0, int64_t row_end = -1) {
+  if (row_end < 0) row_end = num_rows;
+  const int64_t span = row_end - row_begin;
+  if (span <= 0) return SYMPA_OK;
+  const int64_t total = num_pairs * (int64_t)per_s;
+  const int64_t table_bytes = span * (int64_t)per_s * (int64_t)sizeof(double);
+  int64_t passes = (table_bytes + g_scatter_pass_bytes - 1) / g_scatter_pass_bytes;
+  // a pass costs a sweep over the indices of all pairs: no more passes than the batch can pay for
+  const int64_t max_passes = 1 + num_pairs / (num_rows > 0 ? num_rows : 1);
+  if (passes > max_passes) passes = max_passes;
+  if (passes > 16) passes = 16;
+  if (passes < 1) passes = 1;
+  const int64_t rows_per_pass = (span + passes - 1) / passes;
+  for (int64_t lo = row_begin; lo < row_end; lo += rows_per_pass) {
+    const int64_t hi = lo + rows_per_pass < row_end ? lo + rows_per_pass : row_end;
+    scatter_packed_table_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per_s, num_rows, lo, hi, grad_dist, idx, u1, u2,
+                                                                       workspace);
+    const int rc = check_launch();
+    if (rc) return rc;
+  }
+  return SYMPA_OK;
+}
+
 }  // namespace sympa
 
 using namespace sympa;
@@ -411,6 +454,11 @@ int64_t sympa_probe_fp64(int iters, double* out, void* stream) {
 int sympa_set_option(int option, int value) {
   if (option == SYMPA_OPT_SPLIT_PATH) {
     g_split_enabled = value != 0;
+    return SYMPA_OK;
+  }
+  if (option == SYMPA_OPT_SCATTER_PASS_MB) {
+    if (value < 1) return SYMPA_ERR_BAD_ARG;
+    g_scatter_pass_bytes = (int64_t)value << 20;
     return SYMPA_OK;
   }
   return SYMPA_ERR_BAD_ARG;
@@ -629,10 +677,8 @@ int sympa_dist_backward_table(int kind, int n, int metric, int64_t num_pairs, co
   if (cudaMemsetAsync(workspace, 0, (size_t)need, s) != cudaSuccess) return check_launch();
   int rc = SYMPA_OK;
   if (num_pairs > 0) {
-    const int64_t total = num_pairs * (int64_t)per_s;
-    scatter_packed_table_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per_s, num_rows, grad_dist, idx, saved_state,
-                                                                       saved_state + num_pairs * (int64_t)per_s, workspace);
-    rc = check_launch();
+    rc = launch_packed_scatter(num_pairs, per_s, num_rows, grad_dist, idx, saved_state, saved_state + num_pairs * (int64_t)per_s,
+                               workspace, s);
     if (rc) return rc;
   }
   const int64_t tot = num_rows * (int64_t)per;
@@ -662,10 +708,8 @@ int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs, con
   if (cudaMemsetAsync(workspace, 0, (size_t)need, s) != cudaSuccess) return check_launch();
   int rc = SYMPA_OK;
   if (num_pairs > 0) {
-    const int64_t total = num_pairs * (int64_t)per_s;
-    scatter_packed_table_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(total, per_s, num_rows, grad_dist, idx, saved_state,
-                                                                       saved_state + num_pairs * (int64_t)per_s, workspace);
-    rc = check_launch();
+    rc = launch_packed_scatter(num_pairs, per_s, num_rows, grad_dist, idx, saved_state, saved_state + num_pairs * (int64_t)per_s,
+                               workspace, s);
     if (rc) return rc;
     if (grad_wsum_w != nullptr && metric == SYMPA_METRIC_WSUM) {
       if (vvd == nullptr || wsum_w == nullptr) return SYMPA_ERR_BAD_ARG;
@@ -674,6 +718,25 @@ int sympa_table_grad_scatter(int kind, int n, int metric, int64_t num_pairs, con
     }
   }
   return rc;
+}
+
+int sympa_table_grad_scatter_rows(int kind, int n, int64_t num_pairs, const double* grad_dist, const double* saved_state,
+                                  int64_t num_rows, const int64_t* idx, int64_t row_begin, int64_t row_end, double* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  if (!valid_common(kind, n, 0, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (num_rows <= 0 || row_begin < 0 || row_end < row_begin || row_end > num_rows) return SYMPA_ERR_BAD_ARG;
+  const int64_t need = sympa_backward_workspace_bytes(kind, n, num_rows);
+  if (workspace == nullptr || workspace_bytes < need) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs > 0 && (grad_dist == nullptr || saved_state == nullptr || idx == nullptr)) return SYMPA_ERR_BAD_ARG;
+  if (row_end == row_begin) return SYMPA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int per_s = state_doubles(kind, n);
+  if (cudaMemsetAsync(workspace + row_begin * (int64_t)per_s, 0, (size_t)(row_end - row_begin) * per_s * sizeof(double), s) !=
+      cudaSuccess)
+    return check_launch();
+  if (num_pairs == 0) return SYMPA_OK;
+  return launch_packed_scatter(num_pairs, per_s, num_rows, grad_dist, idx, saved_state, saved_state + num_pairs * (int64_t)per_s,
+                               workspace, s, row_begin, row_end);
 }
 
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table, int overwrite,

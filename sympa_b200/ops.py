@@ -257,12 +257,34 @@ class _TableDistFn(torch.autograd.Function):
                 # data-parallel backward: scatter into the packed gradient table, all-reduce (average) THAT - the
                 # one collective of the path, on 62 % of the dense bytes at n = 4 - then write the dense rows
                 need = lib.sympa_backward_workspace_bytes(k, n, rows)
-                if b > 0:
-                    _lib.check(lib.sympa_table_grad_scatter(k, n, m, b, _ptr(grad_dist), _ptr(saved), rows, _ptr(idx.contiguous()),
-                                                            _ptr(vvd), _ptr(w_flat), _ptr(gw), _ptr(ws), ws_bytes, _stream()))
+                if _pipelined_sync():
+                    # scatter the rows in SYNC_SEGMENTS ranges and start the all-reduce of a range as soon as it is
+                    # complete: NCCL works on its own stream while the next range is scattered, so only the last
+                    # range's collective is exposed (the segment count depends on nothing rank-local)
+                    per_s = need // 8 // rows
+                    seg = -(-rows // SYNC_SEGMENTS)
+                    idx_c = idx.contiguous() if b > 0 else None
+                    works = []
+                    for lo in range(0, rows, seg):
+                        hi = min(lo + seg, rows)
+                        _lib.check(lib.sympa_table_grad_scatter_rows(
+                            k, n, b, _ptr(grad_dist) if b > 0 else None, _ptr(saved) if b > 0 else None, rows, _ptr(idx_c),
+                            lo, hi, _ptr(ws), ws_bytes, _stream()))
+                        works.append(_allreduce_avg(ws[lo * per_s: hi * per_s], async_op=True))
+                    if gw is not None and b > 0:
+                        _lib.check(lib.sympa_dist_backward(k, n, m, b, _ptr(grad_dist), _ptr(saved), None, None, None, 0, None,
+                                                           _ptr(vvd), _ptr(w_flat), _ptr(gw), _stream()))
+                    for w in works:
+                        if w is not None:
+                            w.wait()
                 else:
-                    ws[: need // 8].zero_()
-                _allreduce_avg(ws[: need // 8])
+                    if b > 0:
+                        _lib.check(lib.sympa_table_grad_scatter(k, n, m, b, _ptr(grad_dist), _ptr(saved), rows,
+                                                                _ptr(idx.contiguous()), _ptr(vvd), _ptr(w_flat), _ptr(gw), _ptr(ws),
+                                                                ws_bytes, _stream()))
+                    else:
+                        ws[: need // 8].zero_()
+                    _allreduce_avg(ws[: need // 8])
                 _lib.check(lib.sympa_table_grad_expand(k, n, rows, _ptr(ws), _ptr(gt), 1, _stream()))
             else:
                 if b > 0:
@@ -289,15 +311,27 @@ def dist(kind, metric, z1, z2, wsum_w=None):
     return _DistFn.apply(z1, z2, wsum_w, kind, metric)
 
 
-def _allreduce_avg(t):
-    """average over the ranks (what DDP does with the table gradient, train.py:59); no-op in a single process"""
+# ranges the in-backward all-reduce of the packed table gradient is pipelined over (see _TableDistFn.backward)
+SYNC_SEGMENTS = 4
+
+
+def _pipelined_sync():
+    import torch.distributed as dist
+    return (SYNC_SEGMENTS > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and dist.get_backend() == "nccl")
+
+
+def _allreduce_avg(t, async_op=False):
+    """average over the ranks (what DDP does with the table gradient, train.py:59); no-op in a single process.
+    async_op (NCCL only): returns the work handle - the collective is ordered after the kernels already enqueued
+    on the current stream, later kernels do not wait for it until handle.wait()."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         if dist.get_backend() == "nccl":
-            dist.all_reduce(t, op=dist.ReduceOp.AVG)
-        else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            t.div_(dist.get_world_size())
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(dist.get_world_size())
+    return None
 
 
 def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False, by_rows=None):

@@ -34,14 +34,17 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.sympa_version() == 3
+    assert lib.sympa_version() == 4
     assert lib.sympa_error_string(0) == b"ok"
     assert lib.sympa_error_string(2).startswith(b"unsupported")
     # 2 operands * pairs * (2 n n) doubles * 8 bytes
-    # saved state: packed lower triangles for the register-kernel sizes, full blocks for the cooperative ones
+    # saved state: packed lower triangles of the unit gradients, for every kernel family (ABI 4)
     assert lib.sympa_workspace_bytes(0, 4, 1000) == 2 * 1000 * 20 * 8
     assert lib.sympa_workspace_bytes(2, 3, 10) == 2 * 10 * 6 * 8
-    assert lib.sympa_workspace_bytes(0, 10, 10) == 2 * 10 * 200 * 8
+    assert lib.sympa_workspace_bytes(0, 10, 10) == 2 * 10 * 110 * 8
+    # packed gradient table of the table backward: one packed point per row
+    assert lib.sympa_backward_workspace_bytes(0, 10, 1000) == 1000 * 110 * 8
+    assert lib.sympa_backward_workspace_bytes(2, 7, 1000) == 1000 * 28 * 8
     assert lib.sympa_workspace_bytes(0, 11, 10) == -1
     # scratch: only upper n > 4 and batches worth splitting; five n x n planes + n per pair of a chunk, + (1 + n) per pair
     assert lib.sympa_scratch_bytes(0, 10, 1 << 20) == 0        # split path is off by default
@@ -54,6 +57,7 @@ def test_host_only_entry_points(lib):
     finally:
         assert lib.sympa_set_option(1, 0) == 0
     assert lib.sympa_set_option(99, 0) == 1
+    assert lib.sympa_set_option(2, 0) == 1 and lib.sympa_set_option(2, 40) == 0     # scatter pass size in MB
 
 
 def test_argument_errors_are_synchronous(lib):
