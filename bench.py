@@ -484,6 +484,12 @@ def run_ours(args):
     import torch.distributed as dist
     from sympa_b200 import distributed as sd
 
+    # rank 0 prints ONE JSON line on stdout.  NCCL writes its version banner to stdout when the environment sets
+    # NCCL_DEBUG=VERSION/WARN (the GPU boxes do): rather than silencing NCCL, file descriptor 1 points at stderr
+    # until the line is printed, so every library's chatter is kept - on stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = sd.init_process_group()
     assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
     dev = torch.device("cuda", local)
@@ -541,8 +547,11 @@ def run_ours(args):
         out["also"] = extras(args, world, rank, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(kind, n, args.metric, budget_s=args.cpu_budget)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -611,7 +620,7 @@ def dropin_pairs_per_s(dev, n=4, pairs=1 << 21, rows=1 << 20, steps=5):
 
 def _epoch_model(config, dev):
     from types import SimpleNamespace
-    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets, product_tree_grid_triplets
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets, product_cartesian_triplets
     from sympa_b200.model import Model
     torch.manual_seed(0)
     if config == 1:     # BASELINE configs[0]: grid 20x20 (400 nodes, 79 800 pairs), upper / riem / n=2
@@ -620,35 +629,40 @@ def _epoch_model(config, dev):
     elif config == 2:   # BASELINE configs[1]: balanced tree branching 3 height 5 (364 nodes, 66 066 pairs), bounded / fone / n=3
         idx, gd, nodes = balanced_tree_triplets(3, 5)
         a = dict(manifold="bounded", metric="fone", dims=3)
-    else:               # BASELINE configs[2]: product tree(2,4) x grid(4x4) (496 nodes, 122 760 pairs), upper / finf / n=6
-        idx, gd, nodes = product_tree_grid_triplets(2, 4, 4, 2)
+    else:               # BASELINE configs[2]: product-cartesian tree x grid with the reference's CLI defaults (preprocess.py:
+        # tree 3/3 x grid 5x5x5 = 5000 nodes, 12 497 500 pairs), upper / finf / n=6
+        idx, gd, nodes = product_cartesian_triplets(3, 3, 5, 3)
         a = dict(manifold="upper", metric="finf", dims=6)
     args = SimpleNamespace(num_points=nodes, scale_init=1.0, scale_coef=1.0, train_scale=False, **a)
     return Model(args).to(dev), idx.to(dev), gd.to(dev)
 
 
+EPOCH_BATCH = {1: 2048, 2: 2048, 3: 131072}     # configs 1-2: the reference's batch; config 3: 96 steps per epoch
+
+
 def epoch_seconds(dev, world, rank, epochs=3, fused=True, sync_stats=True, config=1):
-    """Seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept), batch 2048, RiemannianSGD."""
+    """Seconds per training epoch (runner.py:90-122 semantics, per-step loss.item() kept), RiemannianSGD."""
     from sympa_b200.optim import RiemannianSGD
     from sympa_b200.runner import train_epoch
     model, idx, gd = _epoch_model(config, dev)
+    bs = EPOCH_BATCH[config]
     opt = RiemannianSGD(model.parameters(), lr=1e-2 * world, fused=fused)
-    train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=0, sync_stats=sync_stats)
+    train_epoch(model, opt, idx, gd, bs, world_size=world, rank=rank, epoch=0, sync_stats=sync_stats)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for ep in range(1, epochs + 1):
-        loss = train_epoch(model, opt, idx, gd, 2048, world_size=world, rank=rank, epoch=ep, sync_stats=sync_stats)
+        loss = train_epoch(model, opt, idx, gd, bs, world_size=world, rank=rank, epoch=ep, sync_stats=sync_stats)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / epochs, loss
 
 
 def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
     """The same epochs on sympa_b200.runner.FusedEpochRunner: two launches per step (fused distortion step, fused
-    optimizer row kernel with clipping and zero_grad), the epoch replayed from a CUDA graph, the loss read back
-    once per epoch."""
+    optimizer row kernel with clipping and zero_grad), the epoch replayed from a CUDA graph on one rank, the loss
+    read back once per epoch."""
     from sympa_b200.runner import FusedEpochRunner
     model, idx, gd = _epoch_model(config, dev)
-    runner = FusedEpochRunner(model, 1e-2 * world, idx, gd, 2048, world_size=world, rank=rank)
+    runner = FusedEpochRunner(model, 1e-2 * world, idx, gd, EPOCH_BATCH[config], world_size=world, rank=rank)
     runner.run_epoch(0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -656,6 +670,59 @@ def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
         loss = runner.run_epoch(ep)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / epochs, loss
+
+
+def cfg4_step(kind, n, metric, dev, world, rank, rows=1 << 20, global_pairs=1 << 22, steps=3):
+    """BASELINE configs[3]: a 1M-node table, one TRAINING STEP (forward, distortion loss, backward, the gradient
+    collective, fused Riemannian SGD update of the table) on a batch of sampled pairs sharded over the ranks.
+    Returns (ms per step, pairs per step, loss of the last step)."""
+    from sympa_b200 import distributed as sd
+    from sympa_b200.embeddings import ManifoldParameter
+    from sympa_b200.losses import AverageDistortionLoss
+    from sympa_b200.optim import RiemannianSGD
+    man = make_manifold(kind, n, metric, dev)
+    table = ManifoldParameter(make_table(kind, n, rows, dev, seed=5), manifold=man)
+    opt = RiemannianSGD([table], lr=1e-3 * world, fused=True)
+    loss_fn = AverageDistortionLoss()
+    b_rank = global_pairs // world
+    chunk = min(chunk_pairs_for(n), b_rank)
+    n_chunks = -(-b_rank // chunk)
+    idx, gd8 = make_pairs(rows, b_rank, dev, seed=500 + rank)
+    gd = gd8.double()
+
+    def step():
+        table.grad = None
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        for c in range(n_chunks):
+            sl = slice(c * chunk, (c + 1) * chunk)
+            d = man.dist_from_table(table, idx[sl], sync_grad=(world > 1 and n_chunks == 1))
+            loss = loss_fn.calculate_loss(gd[sl], d)
+            loss.backward()
+            total += loss.detach()
+        if world > 1 and n_chunks > 1:
+            sd.allreduce_gradients([table.grad], average=True)
+        opt.step()
+        return total
+
+    step()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    out = (ms, global_pairs, float(loss.item()))
+    del table, opt, idx, gd
+    torch.cuda.empty_cache()
+    return out
 
 
 def extras(args, world, rank, dev):
@@ -671,16 +738,33 @@ def extras(args, world, rank, dev):
             out["dropin_how"] = ("upper n=4, 2^21 pairs/step: table[idx] gathers + manifold.dist(z1, z2) on materialised operands "
                                  "+ the reference's loss expression + torch's dense index_put backward (model.py:16-38, "
                                  "losses.py:16-19 as shipped)")
-        for cfg, name in ((1, "config1_grid400_upper_riem_n2"), (2, "config2_tree_b3h5_bounded_fone_n3"),
-                          (3, "config3_product_tree2x4_grid4x4_upper_finf_n6")):
-            sec, loss = epoch_seconds(dev, world, rank, fused=True, sync_stats=True, config=cfg)
-            out[f"train_epoch_sec_{name}_b2048"] = sec
+        # configs 1-2 (79 800 / 66 066 pairs in batches of 2048) do not shard - a 256-pair shard per rank is pure launch
+        # latency: with N > 1 every rank trains its own replica on the whole graph, no collective
+        for cfg, name in ((1, "config1_grid400_upper_riem_n2"), (2, "config2_tree_b3h5_bounded_fone_n3")):
+            tag = "" if world == 1 else "_replica_per_rank"
+            sec, loss = epoch_seconds(dev, 1, 0, fused=True, sync_stats=True, config=cfg)
+            out[f"train_epoch_sec_{name}_b2048{tag}"] = sec
             out[f"train_epoch_final_loss_{name}"] = loss
-            sec_g, loss_g = fused_epoch_seconds(dev, world, rank, config=cfg)
-            out[f"train_epoch_sec_{name}_fused_graph"] = sec_g
+            sec_g, loss_g = fused_epoch_seconds(dev, 1, 0, config=cfg)
+            out[f"train_epoch_sec_{name}_fused_graph{tag}"] = sec_g
             out[f"train_epoch_final_loss_{name}_fused_graph"] = loss_g
-        sec_h, _ = epoch_seconds(dev, world, rank, fused=False, sync_stats=True)
+        sec_h, _ = epoch_seconds(dev, 1, 0, fused=False, sync_stats=True)
         out["train_epoch_sec_config1_host_optimizer"] = sec_h
+        # config 3: product-cartesian graph, 12.5M pairs per epoch, pairs sharded over the ranks, batch 131072
+        name = "config3_product_tree3x3_grid5x5x5_5000nodes_upper_finf_n6_b131072"
+        sec, loss = epoch_seconds(dev, world, rank, epochs=2, fused=True, sync_stats=True, config=3)
+        out[f"train_epoch_sec_{name}_sharded_dp{world}"] = sec
+        out[f"train_epoch_final_loss_{name}"] = loss
+        sec_g, loss_g = fused_epoch_seconds(dev, world, rank, epochs=2, config=3)
+        out[f"train_epoch_sec_{name}_fused_sharded_dp{world}"] = sec_g
+        out[f"train_epoch_final_loss_{name}_fused"] = loss_g
+        # config 4: 1M-node table, one training step on 2^22 sampled pairs (sharded), optimizer included
+        for kind, metric, key in (("upper", "fmin", "cfg4_1Mnodes_upper_fmin_n10"), ("spd", "riem", "cfg4_1Mnodes_spd_n10")):
+            ms, pairs, loss = cfg4_step(kind, 10, metric, dev, world, rank)
+            out[f"{key}_train_step_ms_dp{world}"] = ms
+            out[f"{key}_pairs_per_step"] = pairs
+            out[f"{key}_pairs_per_s"] = pairs / (ms * 1e-3)
+            out[f"{key}_loss"] = loss
     except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -321,4 +321,9 @@ def rsgd_step(kind, p, grad, lr, weight_decay=0.0):
         return upper_projx(p - lr * upper_egrad2rgrad(p, g))
     if kind == "bounded":
         return bounded_projx(p - lr * bounded_egrad2rgrad(p, g))
+    if kind == "spd":
+        # geoopt SymmetricPositiveDefinite (un-vendored; restated from its documented formulas, PARITY UNPINNED):
+        # egrad2rgrad(x, u) = x sym(u) x^T;  retr(x, u) = sym(x + u + u x^-1 u / 2)
+        u = -lr * (p @ sym(g) @ p.transpose(-1, -2))
+        return sym(p + u + 0.5 * u @ torch.linalg.solve(p, u))
     raise ValueError(kind)

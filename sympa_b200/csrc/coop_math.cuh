@@ -325,24 +325,25 @@ SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi, do
   }
   unsigned conv = 0u;
   double c, sr, si, xf;
-  if (loc::jacobi_rotation(*pn, *qn, cr0 + cr1, ci0 - ci1, loc::jacobi_stop_ratio2<N>(), &c, &sr, &si, &xf, &conv)) {
+  // unconditional: a skipped rotation comes back as the identity (c = 1, s = 0, xf = 0) - no divergence between
+  // the groups of a warp in the last sweeps
+  loc::jacobi_rotation_t<loc::jacobi_stop_log2<N>()>(*pn, *qn, cr0 + cr1, ci0 - ci1, &c, &sr, &si, &xf, &conv);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const double a0 = pr[i], b0 = qr[i];
-      if (IS_REAL) {
-        pr[i] = c * a0 - sr * b0;
-        qr[i] = c * b0 + sr * a0;
-      } else {
-        const double a1 = pi[i], b1 = qi[i];
-        pr[i] = c * a0 - (sr * b0 + si * b1);
-        pi[i] = c * a1 - (sr * b1 - si * b0);
-        qr[i] = c * b0 + (sr * a0 - si * a1);
-        qi[i] = c * b1 + (sr * a1 + si * a0);
-      }
+  for (int i = 0; i < N; ++i) {
+    const double a0 = pr[i], b0 = qr[i];
+    if (IS_REAL) {
+      pr[i] = fma(c, a0, -(sr * b0));
+      qr[i] = fma(c, b0, sr * a0);
+    } else {
+      const double a1 = pi[i], b1 = qi[i];
+      pr[i] = fma(c, a0, -fma(si, b1, sr * b0));
+      pi[i] = fma(c, a1, -fma(-si, b0, sr * b1));
+      qr[i] = fma(c, b0, fma(-si, a1, sr * a0));
+      qi[i] = fma(c, b1, fma(si, a0, sr * a1));
     }
-    *pn -= xf;
-    *qn += xf;
   }
+  *pn -= xf;
+  *qn += xf;
   return conv;
 }
 

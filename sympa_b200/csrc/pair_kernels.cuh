@@ -737,9 +737,15 @@ static int launch_mode(int mode, const PairArgs& a, cudaStream_t s) {
 // Riemannian SGD row update (egrad2rgrad + retr + projx fused; upper_half.py:25-66, geoopt RSGD):
 // one thread per table row, rows whose gradient is identically zero are left untouched - which makes
 // the dense launch equivalent to a sparse update of the rows the batch touched.
+// largest matrix size whose optimizer rows run the unrolled (register) templates; above it the rolled
+// local-memory ones
+#ifndef SY_RSGD_REG_MAX_N
+#define SY_RSGD_REG_MAX_N 10
+#endif
 template <int N, int KIND>
 __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
-  constexpr bool REG = N <= SY_REG_MAX_N;
+  // (bounded: the projection carries a full complex Jacobi - unrolled at n = 10 it is a 32 kB stack frame)
+  constexpr bool REG = N <= (KIND == kBounded ? reg_max_n(kBounded) : SY_RSGD_REG_MAX_N);
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = (KIND == kSpd ? 1 : 2) * N * N;
   const double lr = a.lr * (a.lr_scale != nullptr ? __ldg(a.lr_scale) : 1.0);

@@ -293,7 +293,8 @@ def test_split_path_equals_single_kernel_path(sb, n, metric):
 
 
 @pytest.mark.parametrize("kind,metric,n,graph", [("upper", "riem", 2, "grid5"), ("bounded", "fone", 3, "grid5"),
-                                                 ("upper", "riem", 2, "config1"), ("bounded", "fone", 3, "config2")])
+                                                 ("upper", "riem", 2, "config1"), ("bounded", "fone", 3, "config2"),
+                                                 ("upper", "finf", 6, "product")])
 def test_train_epoch_matches_oracle_loop(sb, kind, metric, n, graph):
     """One epoch of the training loop (runner.py:90-122: forward, distortion loss, backward, clip,
     RiemannianSGD) against the same loop driven by the oracle on the CPU: on a small grid graph, and at the
@@ -301,7 +302,7 @@ def test_train_epoch_matches_oracle_loop(sb, kind, metric, n, graph):
     and configs[1] (balanced tree 3/5: 364 nodes, 66 066 pairs, bounded / fone / n = 3, batch 2048)."""
     from types import SimpleNamespace
     from torch.nn.utils import clip_grad_norm_
-    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets
+    from sympa_b200.graphs import balanced_tree_triplets, grid_triplets, product_cartesian_triplets
     from sympa_b200.model import Model
     from sympa_b200.optim import RiemannianSGD
     from sympa_b200.runner import train_epoch
@@ -309,6 +310,8 @@ def test_train_epoch_matches_oracle_loop(sb, kind, metric, n, graph):
     torch.manual_seed(0)
     if graph == "grid5":
         (idx, gd, nodes), bs = grid_triplets(5, 2), 64
+    elif graph == "product":     # BASELINE configs[2] in small: tree(2,3) x grid 3x3 = 135 nodes, 9045 pairs, upper / finf / n = 6
+        (idx, gd, nodes), bs = product_cartesian_triplets(2, 3, 3, 2), 1024
     elif graph == "config1":
         (idx, gd, nodes), bs = grid_triplets(20, 2), 2048
     else:
@@ -378,10 +381,10 @@ def test_fused_rsgd_step_matches_host_optimizer(sb, kind, n, lr):
     untouched = torch.ones(rows, dtype=torch.bool)
     untouched[touched] = False
     assert torch.equal(out[True][untouched], table[untouched])
-    if kind in ("upper", "bounded"):
-        torch.testing.assert_close(out[True], so.rsgd_step(kind, table, grad, lr), rtol=1e-9, atol=1e-11)
-        if lr > 1:
-            assert man.projected_points > 0
+    # the oracle's restatement of the update (spd: geoopt's documented retraction, parity with geoopt itself unpinned)
+    torch.testing.assert_close(out[True], so.rsgd_step(kind, table, grad, lr), rtol=1e-9, atol=1e-11)
+    if kind in ("upper", "bounded") and lr > 1:
+        assert man.projected_points > 0
 
 
 def test_training_with_fused_optimizer_equals_host_optimizer(sb):
