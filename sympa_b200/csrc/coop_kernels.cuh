@@ -21,6 +21,11 @@ struct WarpExec {
   // each lane keeps a top and a bottom column in registers; after every round the top row moves one
   // lane up and the bottom row one lane down with two warp shuffles per value.  Every lane of the
   // warp executes the shuffles (inactive lanes carry garbage that nobody reads).
+  // (Round 2 tried the exchange through shared memory instead - the pair's two G buffers are free while the
+  // columns live in registers; STS.128 / LDS.128 into per-lane slots, ~110 instructions per round against ~290
+  // for the shuffles and their selects - and measured it SLOWER: n = 10 13.6 ms against 11.2 ms per 2^19 pairs,
+  // n = 8 6.4 against 5.2 ms.  Two __syncwarp() and a store -> load round trip per round cost more at 1.25 warps
+  // per scheduler than the shuffles, which pipeline.)
   template <int N, bool IS_REAL>
   __device__ __forceinline__ int jacobi(double* gr, double* gi, double*) const {
     typedef coop::LayoutT<N, 2> L;

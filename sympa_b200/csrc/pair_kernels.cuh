@@ -241,6 +241,10 @@ __device__ __forceinline__ void atomic_add_full(double* __restrict__ out, const 
 #ifndef SY_STAGE_MAX_N
 #define SY_STAGE_MAX_N 4
 #endif
+// 1: every lane gathers the rows of its own pair (stage_rows); 0: the warp gathers row by row, coalesced
+#ifndef SY_STAGE_OWN_ROWS
+#define SY_STAGE_OWN_ROWS 0
+#endif
 
 template <int N, int KIND>
 struct StageCfg {
@@ -322,6 +326,34 @@ __device__ __forceinline__ void stage_rows(const PairArgs& a, int64_t w0, const 
   // compiler fence: the copies below carry no "memory" clobber (see cp_async16), so without it the loads that
   // moved the CURRENT pairs' operands out of the slots could be scheduled after the copies that refill them
   asm volatile("" ::: "memory");
+#if SY_STAGE_OWN_ROWS
+  // Every lane copies the two rows of ITS OWN pair into its own slot: the row addresses sit in the lane's
+  // registers (one LDS.128 of its validated index pair) and the chunk offsets are immediates - no index load
+  // and no address arithmetic per 16-byte chunk.  The price: an instruction touches 32 rows instead of 2-4
+  // (16 of every 32-byte sector per instruction; the other half comes with the next chunk, from L2).
+  {
+    const double* s1;
+    const double* s2;
+    if (a.idx != nullptr) {
+      const longlong2 ij = idxb[lane];
+      s1 = a.table + ij.x * S::PER;
+      s2 = a.table + ij.y * S::PER;
+    } else {
+      int64_t p = w0 + lane;
+      p = p < a.num_pairs ? p : a.num_pairs - 1;
+      s1 = a.z1 + p * S::PER;
+      s2 = a.z2 + p * S::PER;
+    }
+    unsigned char* slot = in + lane * (S::IN_STRIDE * 16);
+#pragma unroll
+    for (int c = 0; c < S::RC; ++c) {
+      cp_async16(slot + c * 16, s1 + 2 * c);
+      cp_async16(slot + (S::RC + c) * 16, s2 + 2 * c);
+    }
+    asm volatile("" ::: "memory");
+    return;
+  }
+#endif
   // flat chunk f = it * 32 + lane among the warp's 32 pairs: pair j = f / (2 RC), then the point
   // (side 0 / 1) and the chunk c within the point
   if (a.idx != nullptr) {

@@ -9,7 +9,7 @@ from .losses import AverageDistortionLoss
 
 
 def train_epoch(model, optimizer, src_dst_ids, graph_distances, batch_size, max_grad_norm=50.0, grad_accum_steps=1,
-                world_size=1, rank=0, epoch=0, shuffle=True, sync_stats=True):
+                world_size=1, rank=0, epoch=0, shuffle=True, sync_stats=True, device_shuffle=False):
     """One pass over the training triplets (runner.py:90-122).
 
     src_dst_ids (T, 2) int64 and graph_distances (T,) live on the device (train.py:95-96).  Each rank
@@ -21,7 +21,9 @@ def train_epoch(model, optimizer, src_dst_ids, graph_distances, batch_size, max_
     """
     loss_fn = AverageDistortionLoss()
     dev = src_dst_ids.device
-    order = sd.shard_indices(src_dst_ids.shape[0], rank, world_size, epoch=epoch, shuffle=shuffle).to(dev)
+    # device_shuffle: the epoch's permutation is drawn on the GPU (not DistributedSampler's CPU order)
+    order = sd.shard_indices(src_dst_ids.shape[0], rank, world_size, epoch=epoch, shuffle=shuffle,
+                             device=dev if device_shuffle else None).to(dev)
     per_rank = max(batch_size // world_size, 1)
     ok, point, reason = model.check_all_points()        # runner.py:91
     if not ok:
@@ -71,14 +73,14 @@ class FusedEpochRunner:
     are updated as Euclidean parameters with the same clipping coefficient (as geoopt's RSGD does)."""
 
     def __init__(self, model, lr, src_dst_ids, graph_distances, batch_size, max_grad_norm=50.0, world_size=1, rank=0,
-                 use_graph=True, shuffle=True):
+                 use_graph=True, shuffle=True, device_shuffle=False):
         table = model.embeddings.embeds
         if not table.is_cuda or table.dtype != torch.float64:
             raise RuntimeError("FusedEpochRunner needs a CUDA float64 embedding table (there is no CPU path)")
         if model.scale.requires_grad:
             raise RuntimeError("FusedEpochRunner: a trainable model scale is not supported, use train_epoch")
         self.model, self.lr, self.max_grad_norm = model, float(lr), float(max_grad_norm)
-        self.world, self.rank, self.shuffle = world_size, rank, shuffle
+        self.world, self.rank, self.shuffle, self.device_shuffle = world_size, rank, shuffle, device_shuffle
         self.ids, self.gdist = src_dst_ids, graph_distances
         self.per_rank = max(batch_size // world_size, 1)
         self.dev = table.device
@@ -86,8 +88,7 @@ class FusedEpochRunner:
         self.kind = man.kind
         self.metric = "riem" if self.kind == "spd" else man.metric.name
         self.wsum = getattr(getattr(man, "metric", None), "weights", None) if self.metric == "wsum" else None
-        shard = sd.shard_indices(src_dst_ids.shape[0], rank, world_size, epoch=0, shuffle=shuffle)
-        self.count = shard.numel()
+        self.count = -(-src_dst_ids.shape[0] // world_size)     # what shard_indices returns (padded by wrapping)
         self.idx_buf = torch.empty(self.count, 2, dtype=torch.int64, device=self.dev)
         self.gd_buf = torch.empty(self.count, dtype=torch.float64, device=self.dev)
         self.grad = torch.zeros_like(table.data)
@@ -129,7 +130,8 @@ class FusedEpochRunner:
         ok, point, reason = self.model.check_all_points()        # runner.py:91
         if not ok:
             raise AssertionError(f"Point outside manifold. Reason: {reason}\n{point}")
-        order = sd.shard_indices(self.ids.shape[0], self.rank, self.world, epoch=epoch, shuffle=self.shuffle).to(self.dev)
+        order = sd.shard_indices(self.ids.shape[0], self.rank, self.world, epoch=epoch, shuffle=self.shuffle,
+                                 device=self.dev if self.device_shuffle else None).to(self.dev)
         torch.index_select(self.ids, 0, order, out=self.idx_buf)
         torch.index_select(self.gdist, 0, order, out=self.gd_buf)
         self.loss_acc.zero_()
