@@ -47,11 +47,10 @@ def algorithmic_bytes_per_pair(kind, n):
 
 def kernel_bytes_per_pair(kind, n):
     """the forward + unit-gradient kernel ALONE: two rows in, two index words, dist + vvd out, and the saved unit
-    gradients out (packed lower triangles for the register kernels, full blocks for the cooperative ones)"""
+    gradients out (packed lower triangles)"""
     blocks = 1 if kind == "spd" else 2
     rows_in = 2 * blocks * n * n * 8
-    packed = n <= {"upper": 6, "bounded": 7, "spd": 10}[kind]
-    state = 2 * blocks * (n * (n + 1) // 2 if packed else n * n) * 8
+    state = 2 * blocks * (n * (n + 1) // 2) * 8       # packed lower triangles, every kernel family (ABI 4)
     return rows_in + state + 16 + 8 * n + 8
 
 
@@ -187,15 +186,18 @@ def make_manifold(kind, n, metric, dev):
         dims=n, metric=MetricType.from_str(metric)).to(dev)
 
 
-def our_launches_per_chunk(kind, n, rows, b, dev, world):
+def our_launches_per_chunk(kind, n, rows, b, dev, world, single_chunk=True):
     """kernels of libsympa_b200.so one chunk launches through the public API: forward + unit gradients, loss forward
-    and backward, table-gradient backward (packed scatter + expansion, or the direct scatter); the bounded domain
-    by rows adds its two row kernels.  torch's own fill / add kernels are not counted."""
+    and backward, table-gradient backward (packed scatter + expansion, or the direct scatter; with the in-backward
+    all-reduce of a multi-rank run the scatter is one launch per pipelined row segment); the bounded domain by rows
+    adds its two row kernels.  torch's own fill / add kernels and NCCL's are not counted."""
     from sympa_b200 import ops
-    by_rows = ops.bounded_by_rows(kind, n, b, rows, world > 1)
+    sync = world > 1 and single_chunk
+    by_rows = ops.bounded_by_rows(kind, n, b, rows, sync)
     kk = "upper" if by_rows else kind
-    packed = ops.backward_workspace_for(kk, n, rows, dev)[1] > 0 and (2 * b >= rows or world > 1)
-    return 1 + 2 + (2 if packed else 1) + (2 if by_rows else 0)
+    packed = ops.backward_workspace_for(kk, n, rows, dev)[1] > 0 and (2 * b >= rows or sync)
+    scatter = (ops.SYNC_SEGMENTS + 1) if (sync and packed) else (2 if packed else 1)
+    return 1 + 2 + scatter + (2 if by_rows else 0)
 
 
 def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, local, dev, per_kernel=True, fused=True,
@@ -272,38 +274,61 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
     clocks = sampler.stop()
     res = {"value": global_pairs * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "clocks": clocks,
            "pairs_per_gpu_per_step": b_rank, "chunk_pairs": chunk, "chunks_per_step": n_chunks}
-    lpc = our_launches_per_chunk(kind, n, rows, chunk, dev, world)
+    lpc = our_launches_per_chunk(kind, n, rows, chunk, dev, world, single_chunk=(n_chunks == 1))
     res["gpu_launches"] = lpc * n_chunks * steps
     res["launches_per_chunk"] = lpc
 
     lib = _lib.load()
     if per_kernel:   # the kernels of one chunk timed alone, CUDA events on the launching (current) stream
-        fwd_ms, bwd_ms = [], []
+        fwd_ms, bwd_ms, rows_ms = [], [], []
         ci, cg = resident_chunk(0)
         cb = ci.shape[0]
-        ws, ws_bytes = ops.backward_workspace_for(kind, n, rows, dev)
+        # the route the step takes: bounded by rows = row transform + the UPPER-half pair kernel on the transformed table
+        by_rows = ops.bounded_by_rows(kind, n, cb, rows, world > 1 and n_chunks == 1)
+        kk = "upper" if by_rows else kind
+        ktable = table.detach()
+        if by_rows:
+            ktable = torch.empty_like(ktable)
+            gz = torch.empty_like(ktable)
+        ws, ws_bytes = ops.backward_workspace_for(kk, n, rows, dev)
         gt = torch.empty_like(table)
+        stream = torch.cuda.current_stream().cuda_stream
         for _ in range(min(steps, 10)):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+            if by_rows:
+                ev[4].record()
+                _lib.check(lib.sympa_bounded_rows_to_upper(n, rows, table.data_ptr(), ktable.data_ptr(),
+                                                           ops.status_word(dev).data_ptr(), stream))
+                ev[5].record()
             with torch.no_grad():
                 ev[0].record()
-                dd, vv, saved = ops.forward_raw(kind, mk, table=table.detach(), idx=ci, wsum_w=None, want_grad=True)
+                dd, vv, saved = ops.forward_raw(kk, mk, table=ktable, idx=ci, wsum_w=None, want_grad=True)
                 ev[1].record()
             g1 = torch.ones_like(dd)
             ev[2].record()   # the backward of the table path as the autograd Function issues it (workspace, overwrite)
-            _lib.check(lib.sympa_dist_backward_table(_lib.KIND[kind], n, _lib.METRIC["riem"], cb, g1.data_ptr(),
+            _lib.check(lib.sympa_dist_backward_table(_lib.KIND[kk], n, _lib.METRIC["riem"], cb, g1.data_ptr(),
                                                      saved.data_ptr(), gt.data_ptr(), rows, ci.data_ptr(), None, None, None,
                                                      None if ws is None else ws.data_ptr(), ws_bytes, 1,
                                                      torch.cuda.current_stream().cuda_stream))
             ev[3].record()
+            if by_rows:
+                ev[6].record()
+                _lib.check(lib.sympa_bounded_rows_backward(n, rows, table.data_ptr(), gt.data_ptr(), gz.data_ptr(), 1, stream))
+                ev[7].record()
             torch.cuda.synchronize()
             fwd_ms.append(ev[0].elapsed_time(ev[1]))
             bwd_ms.append(ev[2].elapsed_time(ev[3]))
+            if by_rows:
+                rows_ms.append(ev[4].elapsed_time(ev[5]) + ev[6].elapsed_time(ev[7]))
             del saved, dd, vv
         del gt
         res["kernel_ms"] = statistics.mean(fwd_ms)
         res["backward_ms"] = statistics.mean(bwd_ms)
         res["kernel_pairs"] = cb
+        res["kernel_kind"] = kk
+        if by_rows:
+            res["bounded_rows_ms"] = statistics.mean(rows_ms)
+            del ktable, gz
 
     if fused:    # one launch per chunk (on-device loss): sympa_distortion_step
         gtab = torch.zeros_like(table)
@@ -392,8 +417,9 @@ def roofline_of(kind, n, res, fp64_peak, fp64_clocks, peaks, peak_src, rows):
     kb = kernel_bytes_per_pair(kind, n) * b
     step_b = res["pairs_per_gpu_per_step"]
     step_s = res["ms_per_step"] * 1e-3
-    coop = n > {"upper": 6, "bounded": 7, "spd": 10}[kind]
-    kname = (f"coop_kernel<{n},{kind},fwd+unit-grad>" if coop else f"pair_kernel<{n},{kind},fwd+unit-grad>")
+    kk = res.get("kernel_kind", kind)
+    coop = n > {"upper": 7, "bounded": 7, "spd": 10}[kk]
+    kname = (f"coop_kernel<{n},{kk},fwd+unit-grad>" if coop else f"pair_kernel<{n},{kk},fwd+unit-grad>")
     fp64_bound = n >= 3
     traffic = scatter = None
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
@@ -428,6 +454,10 @@ def roofline_of(kind, n, res, fp64_peak, fp64_clocks, peaks, peak_src, rows):
                      "how": "F_lean resp. SURVEY.md 8(d) bytes (64n^2+8n+32) x this GPU's pairs of a step / device time of the "
                             "whole step (forward, loss, backward scatter + expansion, gradient accumulation, collective)"},
                  "backward_ms": round(res["backward_ms"], 4)})
+    if "bounded_rows_ms" in res:
+        main["bounded_rows_ms"] = round(res["bounded_rows_ms"], 4)
+        main["note"] = ("bounded domain by rows: the inverse Cayley transform runs once per table row and chunk "
+                        "(sympa_bounded_rows_to_upper / _backward, bounded_rows_ms), the pairs run the upper-half kernel")
     if scatter is not None:
         main["scatter"] = scatter
     return main

@@ -858,9 +858,15 @@ int launch_rsgd(int kind, const RsgdArgs& a, cudaStream_t s) {
   return check_launch();
 }
 
+// largest matrix size whose row transforms run the unrolled templates (round 1 stopped at 7 and left the larger
+// bounded sizes on the per-pair cooperative kernel with its 12 shared-memory buffers; unrolled, the rows of n = 10
+// cost two real SPD inversions and one complex sandwich per ROW, and the pairs run the upper-half kernel)
+#ifndef SY_BOUNDED_ROWS_REG_MAX_N
+#define SY_BOUNDED_ROWS_REG_MAX_N 10
+#endif
 template <int N, bool BACKWARD>
 __global__ void __launch_bounds__(kThreads) bounded_rows_kernel(const BoundedRowsArgs a) {
-  constexpr bool REG = N <= reg_max_n(kBounded);
+  constexpr bool REG = N <= SY_BOUNDED_ROWS_REG_MAX_N;
   constexpr int T = Cfg<N>::kTri;
   constexpr int PER = 2 * N * N;
   unsigned st = 0;

@@ -10,6 +10,9 @@ from . import _lib
 # bounded domain on the table path: transform the rows once instead of both operands of every pair when the
 # batch covers the table densely (set to False to force the per-pair bounded kernels)
 BOUNDED_BY_ROWS = True
+# largest matrix size of that route (the row kernels are unrolled register code for every n since round 2;
+# round 1 stopped at 7: its rolled local-memory row kernels made bounded n = 10 slower, 18.9 -> 8.2 M pairs/s)
+BOUNDED_BY_ROWS_MAX_N = 10
 
 _status_words = {}
 _scratch = {}
@@ -194,7 +197,7 @@ def bounded_by_rows(kind, n, num_pairs, num_rows, sync_grad):
     multi-process group the choice must not depend on rank-local state - the ranks put their result into ONE
     all-reduced buffer, and the by-rows route accumulates the gradient with respect to the TRANSFORMED rows -
     so there it depends on (kind, n) only; a single process also looks at how densely the batch covers the table."""
-    if not (BOUNDED_BY_ROWS and kind == "bounded" and n <= 7 and num_rows > 0):
+    if not (BOUNDED_BY_ROWS and kind == "bounded" and n <= BOUNDED_BY_ROWS_MAX_N and num_rows > 0):
         return False
     if sync_grad and _world_size() > 1:
         return True
@@ -211,9 +214,7 @@ class _TableDistFn(torch.autograd.Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         # bounded domain, batch covering the table densely: the inverse Cayley transform is applied once per
         # table row (sympa_bounded_rows_to_upper) and the pairs run the upper-half kernels on the result
-        # (break-even in flops is 2 pairs per row.  Only for n <= 7, where the row kernels are the unrolled register
-        # code: the rolled local-memory row kernels of the larger sizes measured far slower than they save -
-        # bounded n = 10 18.9 -> 8.2 M pairs/s on a 2^20-row table)
+        # (break-even in flops is 2 pairs per row)
         if by_rows is None:
             by_rows = table.is_cuda and idx.dim() == 2 and bounded_by_rows(kind, table.shape[-1], idx.shape[0],
                                                                            table.shape[0], sync_grad)
