@@ -854,7 +854,7 @@ def cpu_baseline(kind, n, metric, budget_s=15.0, threads=None):
         step()
         reps += 1
         el = time.perf_counter() - t0
-        if el > budget_s or reps >= 50:
+        if el > budget_s or reps >= 2000:
             break
     return {"value": b * reps / el, "unit": "pairs/s", "cores": threads, "kind": label,
             "sample": f"{reps} steps x {b} pairs of the same workload ({kind} n={n} metric={metric}, table 2^14 rows), "
