@@ -705,7 +705,7 @@ def fused_epoch_seconds(dev, world, rank, epochs=5, config=1):
     return (time.perf_counter() - t0) / epochs, loss
 
 
-def cfg4_step(kind, n, metric, dev, world, rank, rows=1 << 20, global_pairs=1 << 22, steps=3):
+def cfg4_step(kind, n, metric, dev, world, rank, rows=1 << 20, global_pairs=1 << 22, steps=3, owner_computes=False):
     """BASELINE configs[3]: a 1M-node table, one TRAINING STEP (forward, distortion loss, backward, the gradient
     collective, fused Riemannian SGD update of the table) on a batch of sampled pairs sharded over the ranks.
     Returns (ms per step, pairs per step, loss of the last step)."""
@@ -723,16 +723,24 @@ def cfg4_step(kind, n, metric, dev, world, rank, rows=1 << 20, global_pairs=1 <<
     idx, gd8 = make_pairs(rows, b_rank, dev, seed=500 + rank)
     gd = gd8.double()
 
+    from sympa_b200 import ops
+    lr = 1e-3 * world
+
     def step():
         table.grad = None
         total = torch.zeros((), dtype=torch.float64, device=dev)
+        in_backward = world > 1 and n_chunks == 1 and not owner_computes
         for c in range(n_chunks):
             sl = slice(c * chunk, (c + 1) * chunk)
-            d = man.dist_from_table(table, idx[sl], sync_grad=(world > 1 and n_chunks == 1))
+            d = man.dist_from_table(table, idx[sl], sync_grad=in_backward)
             loss = loss_fn.calculate_loss(gd[sl], d)
             loss.backward()
             total += loss.detach()
-        if world > 1 and n_chunks > 1:
+        if owner_computes and world > 1:
+            # reduce-scatter by row owner, fused update of the owned rows, all-gather
+            sd.sharded_rsgd_step(table, lr, lambda t, g, s: ops.rsgd_step(kind, t, g.contiguous(), s))
+            return total
+        if world > 1 and not in_backward:
             sd.allreduce_gradients([table.grad], average=True)
         opt.step()
         return total
@@ -798,6 +806,10 @@ def extras(args, world, rank, dev):
             out[f"{key}_pairs_per_step"] = pairs
             out[f"{key}_pairs_per_s"] = pairs / (ms * 1e-3)
             out[f"{key}_loss"] = loss
+            if world > 1:   # the same step with the owner-computes optimizer (reduce-scatter, update of N/P rows, all-gather)
+                ms2, _, loss2 = cfg4_step(kind, 10, metric, dev, world, rank, owner_computes=True)
+                out[f"{key}_train_step_ms_dp{world}_owner_computes"] = ms2
+                out[f"{key}_loss_owner_computes"] = loss2
     except Exception as e:  # noqa: BLE001 - extras must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -1,0 +1,17 @@
+#!/bin/bash
+# multi-GPU check: gpurun --gpus N -- 'bash profiles/r02_multigpu.sh N'
+cd $GRAFT_REPO_ROOT
+N=${1:-2}
+nvidia-smi -L | head -8
+python -m pytest tests/test_multigpu_nccl.py -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
+grep -v "UserWarning\|return func\|^$\|\*\*\*\*\|OMP_NUM" gpurun_out/r02_bench_n$N.err | tail -8
+python -c "
+import json
+d=json.load(open('gpurun_out/r02_bench_n$N.json'))
+print('value %.4e ms/step %.3f e2e %.4e (%.3f ms)' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step']))
+print('parity', d.get('parity_check',{}).get('ok'), d.get('parity_check',{}).get('max_rel'))
+print('n10 %.4e e2e %.4e' % (d['n10']['value'], d['n10']['e2e']['value']))
+print('launches', d['gpu_launches'], d['gpu_launches_how'][:90])
+for k,v in d.get('also',{}).items(): print(' ', k, v)
+"
