@@ -355,7 +355,9 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
         # on the device by the feeder; every chunk of every step crosses PCIe inside the timed region
         idx_h = idx.to(torch.int32).cpu().pin_memory()
         gd_h = gd8.cpu().pin_memory()
-        loss_h = torch.empty(1, dtype=torch.float64).pin_memory()
+        loss_h = torch.empty(2, dtype=torch.float64).pin_memory()    # two slots: the host reads step k - 1 while step k runs
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        losses = []
         feeder = PairFeeder(dev)
 
         def submit(c):
@@ -376,14 +378,24 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
                 return ic, gc
             total = run_chunks(get)
             feeder.done()
-            loss_h.copy_(total.reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return float(loss_h[0])
+            k = step_no[0] % 2
+            loss_h[k:k + 1].copy_(total.reshape(1), non_blocking=True)      # this step's result, device -> host
+            loss_ev[k].record()
+            if step_no[0] > 0:      # block on the PREVIOUS step's read-back: the host stays one step ahead of the device
+                loss_ev[1 - k].synchronize()
+                losses.append(float(loss_h[1 - k]))
+            step_no[0] += 1
+
+        step_no = [0]
 
         def run_e2e(k):
+            step_no[0] = 0
             submit(0)                       # first chunk: its copy is exposed, and inside the timed region
             for s in range(k):
                 step_e2e(s + 1 < k)
+            last = (k - 1) % 2              # the last step's loss: the host waits for it inside the timed region
+            loss_ev[last].synchronize()
+            losses.append(float(loss_h[last]))
 
         run_e2e(2)
         barrier()
@@ -401,7 +413,8 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
                              "through the public API; the chunk's index pairs (int32 on the host, widened on the device) and "
                              "graph distances (uint8 on the host) are copied from pinned host memory by "
                              "sympa_b200.feeder.PairFeeder (the copy of chunk k+1 overlaps the compute of chunk k on a side "
-                             "stream; the first copy is exposed), the step's loss is read back and the host waits for it"}
+                             "stream; the first copy is exposed); every step's loss is copied device -> host, the host waits for the read-back of "
+                             "step k - 1 after enqueueing step k (and for the last step's before the timed region ends)"}
         del idx_h, gd_h
     ops.check_status(dev)
     del table, idx, gd

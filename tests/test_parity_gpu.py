@@ -698,3 +698,39 @@ def test_bounded_row_kernels_large_n(sb, n):
     ref = so.sym(zr.grad)
     assert (gz.cpu() - ref).abs().max().item() <= 1e-9 * ref.abs().max().item()
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 4), ("upper", 10), ("spd", 5)])
+def test_table_grad_scatter_rows_equals_full_scatter(sb, kind, n):
+    """sympa_table_grad_scatter_rows over a partition of the rows (what a pipelined data-parallel backward calls,
+    one range at a time) fills the packed gradient table exactly like sympa_table_grad_scatter; an empty batch
+    only zeroes its range."""
+    from sympa_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(31 + n)
+    rows, pairs = 97, 700
+    table = (so.spd_spread(rows, n, generator=g) if kind == "spd" else so.upper_spread(rows, n, generator=g, scale=0.3)).cuda()
+    src = torch.randint(0, rows, (pairs,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (pairs,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    gdist = torch.rand(pairs, dtype=torch.float64, generator=g).cuda() + 0.5
+    _, _, saved = sb.ops.forward_raw(kind, "riem", table=table, idx=idx, want_grad=True)
+    k = _lib.KIND[kind]
+    need = lib.sympa_backward_workspace_bytes(k, n, rows)
+    assert need == rows * (1 if kind == "spd" else 2) * (n * (n + 1) // 2) * 8
+    stream = torch.cuda.current_stream().cuda_stream
+    full = torch.full((need // 8,), 7.0, dtype=torch.float64, device="cuda")
+    _lib.check(lib.sympa_table_grad_scatter(k, n, 0, pairs, gdist.data_ptr(), saved.data_ptr(), rows, idx.data_ptr(), None, None,
+                                            None, full.data_ptr(), need, stream))
+    parts = torch.full((need // 8,), -3.0, dtype=torch.float64, device="cuda")
+    for lo, hi in ((0, 10), (10, 64), (64, 64), (64, rows)):
+        _lib.check(lib.sympa_table_grad_scatter_rows(k, n, pairs, gdist.data_ptr(), saved.data_ptr(), rows, idx.data_ptr(), lo, hi,
+                                                     parts.data_ptr(), need, stream))
+    torch.testing.assert_close(parts, full, rtol=1e-12, atol=1e-12 * full.abs().max().item())   # atomics: order differs
+    per_s = need // 8 // rows
+    _lib.check(lib.sympa_table_grad_scatter_rows(k, n, 0, None, None, rows, None, 5, 9, parts.data_ptr(), need, stream))
+    assert float(parts[5 * per_s: 9 * per_s].abs().max()) == 0.0
+    torch.testing.assert_close(parts[9 * per_s:], full[9 * per_s:], rtol=1e-12, atol=1e-12 * full.abs().max().item())
+    assert lib.sympa_table_grad_scatter_rows(k, n, pairs, gdist.data_ptr(), saved.data_ptr(), rows, idx.data_ptr(), 5, rows + 1,
+                                             parts.data_ptr(), need, stream) == 1      # range outside the table
+    sb.ops.check_status()
