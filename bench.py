@@ -196,7 +196,9 @@ def our_launches_per_chunk(kind, n, rows, b, dev, world, single_chunk=True):
     by_rows = ops.bounded_by_rows(kind, n, b, rows, sync)
     kk = "upper" if by_rows else kind
     packed = ops.backward_workspace_for(kk, n, rows, dev)[1] > 0 and (2 * b >= rows or sync)
-    scatter = (ops.SYNC_SEGMENTS + 1) if (sync and packed) else (2 if packed else 1)
+    scatter = (ops.SYNC_SEGMENTS + 1) if (sync and packed and ops.SYNC_SEGMENTS > 1) else (2 if packed else 1)
+    if not single_chunk:     # gradient accumulation: scatter per chunk; expansion and row transforms once per step
+        return 1 + 2 + 1
     return 1 + 2 + scatter + (2 if by_rows else 0)
 
 
@@ -232,20 +234,24 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
             ms = t.item()
         return ms
 
+    # a shard of several chunks is one step with gradient accumulation (the reference's grad_accum_steps,
+    # runner.py:104): the chunks share a packed gradient table, expanded (and all-reduced) once per step
+    acc = man.table_grad_accumulator(table) if n_chunks > 1 else None
+
     def run_chunks(get_chunk):
-        """one step: every chunk through the public API; the table gradient accumulates in table.grad, the one
-        collective of the step follows the last backward (inside it, on the packed gradient table, when the
-        shard is a single chunk)"""
+        """one step: every chunk through the public API; one chunk: the collective runs inside its backward on the
+        packed gradient table; several chunks: they accumulate in the packed table of `acc`, and acc.finish() runs
+        the collective on it and writes table.grad"""
         table.grad = None
         total = torch.zeros((), dtype=torch.float64, device=dev)
         for c in range(n_chunks):
             idx_c, gd_c = get_chunk(c)
-            d = man.dist_from_table(table, idx_c, sync_grad=(world > 1 and n_chunks == 1))
+            d = man.dist_from_table(table, idx_c, sync_grad=(world > 1 and acc is None), accumulator=acc)
             loss = loss_fn.calculate_loss(gd_c, d * scale)
             loss.backward()
             total += loss.detach()
-        if world > 1 and n_chunks > 1:
-            sd.allreduce_gradients([table.grad], average=True)
+        if acc is not None:
+            acc.finish(sync_grad=world > 1)
         return total
 
     def resident_chunk(c):
@@ -254,13 +260,18 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
     def step_resident():
         return run_chunks(resident_chunk)
 
-    def timed(fn, k):
+    host_ms = {}
+
+    def timed(fn, k, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(k):
             fn()
         e1.record()
+        if tag:      # host time to ENQUEUE the steps (no synchronisation inside): must stay below the device time
+            host_ms[tag] = (time.perf_counter() - t0) * 1e3 / k
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
@@ -270,12 +281,14 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.2)
-    ms_total = timed(step_resident, steps)
+    ms_total = timed(step_resident, steps, tag="resident")
     clocks = sampler.stop()
     res = {"value": global_pairs * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "clocks": clocks,
+           "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
            "pairs_per_gpu_per_step": b_rank, "chunk_pairs": chunk, "chunks_per_step": n_chunks}
     lpc = our_launches_per_chunk(kind, n, rows, chunk, dev, world, single_chunk=(n_chunks == 1))
-    res["gpu_launches"] = lpc * n_chunks * steps
+    per_step_extra = 0 if n_chunks == 1 else (1 + (2 if kind == "bounded" else 0))     # expansion (+ row transforms) once per step
+    res["gpu_launches"] = (lpc * n_chunks + per_step_extra) * steps
     res["launches_per_chunk"] = lpc
 
     lib = _lib.load()
@@ -567,8 +580,10 @@ def run_ours(args):
         "gpu_launches": res["gpu_launches"],
         "gpu_launches_how": f"{res['launches_per_chunk']} kernels of libsympa_b200.so per chunk x {res['chunks_per_step']} "
                             f"chunks x {args.steps} steps (forward + unit gradients, loss forward, loss backward, table-gradient "
-                            "scatter [+ expansion]); torch's fill / accumulate kernels and NCCL's are not counted",
+                            "scatter [+ expansion, once per step when the chunks accumulate]); torch's fill kernels and NCCL's are not "
+                            "counted",
         "fused_step": res["fused_step"],
+        "host_enqueue_ms_per_step": res["host_enqueue_ms_per_step"],
         "clocks": res["clocks"],
         "roofline": roofline,
     }

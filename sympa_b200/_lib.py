@@ -39,6 +39,7 @@ EXPORTS = (
     "sympa_table_grad_scatter",
     "sympa_table_grad_expand",
     "sympa_table_grad_scatter_rows",
+    "sympa_table_grad_scatter_add",
     "sympa_distortion_loss_forward",
     "sympa_distortion_loss_backward",
     "sympa_bounded_rows_to_upper",
@@ -94,6 +95,8 @@ def load():
     lib.sympa_table_grad_scatter.argtypes = [I, I, I, L, P, P, L, P, P, P, P, P, L, P]
     lib.sympa_table_grad_scatter_rows.restype = I
     lib.sympa_table_grad_scatter_rows.argtypes = [I, I, L, P, P, L, P, L, L, P, L, P]
+    lib.sympa_table_grad_scatter_add.restype = I
+    lib.sympa_table_grad_scatter_add.argtypes = [I, I, L, P, P, L, P, P, L, P]
     lib.sympa_table_grad_expand.restype = I
     lib.sympa_table_grad_expand.argtypes = [I, I, L, P, P, I, P]
     lib.sympa_distortion_loss_forward.restype = I

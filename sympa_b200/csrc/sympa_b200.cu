@@ -739,6 +739,19 @@ int sympa_table_grad_scatter_rows(int kind, int n, int64_t num_pairs, const doub
                                workspace, s, row_begin, row_end);
 }
 
+int sympa_table_grad_scatter_add(int kind, int n, int64_t num_pairs, const double* grad_dist, const double* saved_state,
+                                 int64_t num_rows, const int64_t* idx, double* workspace, int64_t workspace_bytes, void* stream) {
+  if (!valid_common(kind, n, 0, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
+  if (num_rows <= 0) return SYMPA_ERR_BAD_ARG;
+  const int64_t need = sympa_backward_workspace_bytes(kind, n, num_rows);
+  if (workspace == nullptr || workspace_bytes < need) return SYMPA_ERR_BAD_ARG;
+  if (num_pairs == 0) return SYMPA_OK;
+  if (grad_dist == nullptr || saved_state == nullptr || idx == nullptr) return SYMPA_ERR_BAD_ARG;
+  const int per_s = state_doubles(kind, n);
+  return launch_packed_scatter(num_pairs, per_s, num_rows, grad_dist, idx, saved_state, saved_state + num_pairs * (int64_t)per_s,
+                               workspace, (cudaStream_t)stream);
+}
+
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table, int overwrite,
                             void* stream) {
   if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;

@@ -54,12 +54,18 @@ class SiegelManifold(Manifold, ABC):
             _, v, _ = ops.forward_raw(self.kind, self.metric.name, z1=z1, z2=z2, wsum_w=self._wsum(z1))
         return v
 
-    def dist_from_table(self, table: torch.Tensor, idx: torch.Tensor, sync_grad: bool = False) -> torch.Tensor:
+    def dist_from_table(self, table: torch.Tensor, idx: torch.Tensor, sync_grad: bool = False, accumulator=None) -> torch.Tensor:
         """dist(table[idx[:, 0]], table[idx[:, 1]]) with the gather and its backward fused
         (replaces sympa/embeddings.py:29-34 + model.py:26-38).  sync_grad=True makes the backward average the
-        table gradient over the ranks itself (on the packed gradient table): do not all-reduce it again."""
-        d, _ = ops.table_dist(self.kind, self.metric.name, table, idx, self._wsum(table), sync_grad=sync_grad)
+        table gradient over the ranks itself (on the packed gradient table): do not all-reduce it again.
+        accumulator: a `table_grad_accumulator(table)` shared by the calls of one step (gradient accumulation)."""
+        d, _ = ops.table_dist(self.kind, self.metric.name, table, idx, self._wsum(table), sync_grad=sync_grad,
+                              accumulator=accumulator)
         return d
+
+    def table_grad_accumulator(self, table: torch.Tensor):
+        """see sympa_b200.ops.TableGradAccumulator"""
+        return ops.TableGradAccumulator(self.kind, table)
 
     def dist_matrix(self, table: torch.Tensor, row_begin: int = 0, row_count=None) -> torch.Tensor:
         """All-pairs distances between the rows of `table` (rows [row_begin, row_begin + row_count) of the

@@ -34,9 +34,13 @@ class SymmetricPositiveDefinite(Manifold):
             _, v, _ = ops.forward_raw("spd", "riem", z1=x, z2=y)
         return v
 
-    def dist_from_table(self, table, idx, sync_grad=False):
-        d, _ = ops.table_dist("spd", "riem", table, idx, sync_grad=sync_grad)
+    def dist_from_table(self, table, idx, sync_grad=False, accumulator=None):
+        d, _ = ops.table_dist("spd", "riem", table, idx, sync_grad=sync_grad, accumulator=accumulator)
         return d
+
+    def table_grad_accumulator(self, table):
+        """see sympa_b200.ops.TableGradAccumulator"""
+        return ops.TableGradAccumulator("spd", table)
 
     def dist_matrix(self, table, row_begin=0, row_count=None):
         """all-pairs distances between the rows of `table` (see SiegelManifold.dist_matrix)"""

@@ -204,14 +204,85 @@ def bounded_by_rows(kind, n, num_pairs, num_rows, sync_grad):
     return 2 * num_pairs >= num_rows
 
 
+class TableGradAccumulator:
+    """Gradient accumulation over the dist_from_table calls of ONE step (the reference's grad_accum_steps,
+    runner.py:104): the backward of every call scatter-adds into one packed gradient table, and finish() - once
+    per step - runs the collective on it (optional), expands it into table.grad and zeroes it for the next step.
+    Saves, per call after the first, the zeroing and expansion passes over the table and autograd's dense
+    accumulation (0.26 ms of a 5.1 ms chunk at n = 4 and 2^20 rows), keeps the all-reduce of a multi-chunk step on
+    the packed bytes, and - bounded domain by rows - transforms the table once per step instead of once per call
+    (the transformed table is cached until finish(), or until the table is modified in place).
+
+        acc = manifold.table_grad_accumulator(table)
+        for idx_c, gd_c in chunks:
+            loss_fn.calculate_loss(gd_c, manifold.dist_from_table(table, idx_c, accumulator=acc)).backward()
+        acc.finish(sync_grad=world_size > 1)       # table.grad is ready (accumulated into if it already existed)
+    """
+
+    def __init__(self, kind, table):
+        lib = _lib.load()
+        self.table = table
+        self.n, self.rows = table.shape[-1], table.shape[0]
+        _check_n(self.n)
+        self.by_rows = bool(BOUNDED_BY_ROWS and kind == "bounded" and self.n <= BOUNDED_BY_ROWS_MAX_N)
+        self.kind = "upper" if self.by_rows else kind
+        self.nbytes = lib.sympa_backward_workspace_bytes(_lib.KIND[self.kind], self.n, self.rows)
+        self.ws = torch.zeros(self.nbytes // 8, dtype=torch.float64, device=table.device)
+        self._src = self._src_of = None
+        self._src_version = -1
+
+    def source(self):
+        """the table the pair kernels read: the table itself, or its inverse Cayley transform (cached per version)"""
+        if not self.by_rows:
+            return _require(self.table, "table").detach()
+        if self._src is None or self._src_version != self.table._version:
+            t = _require(self.table, "table").detach()
+            src = torch.empty_like(t) if self._src is None else self._src
+            with torch.cuda.device(t.device):
+                _lib.check(_lib.load().sympa_bounded_rows_to_upper(self.n, self.rows, _ptr(t), _ptr(src),
+                                                                   _ptr(status_word(t.device)), _stream()))
+            self._src, self._src_of, self._src_version = src, t, self.table._version
+        return self._src
+
+    def finish(self, sync_grad=False):
+        lib = _lib.load()
+        dev = self.table.device
+        with torch.cuda.device(dev):
+            if sync_grad:
+                _allreduce_avg(self.ws)
+            gt = torch.empty(self.table.shape, dtype=torch.float64, device=dev)
+            _lib.check(lib.sympa_table_grad_expand(_lib.KIND[self.kind], self.n, self.rows, _ptr(self.ws), _ptr(gt), 1, _stream()))
+            if self.by_rows:
+                src_of = self._src_of if self._src_of is not None else _require(self.table, "table").detach()
+                gz = torch.empty_like(gt)
+                _lib.check(lib.sympa_bounded_rows_backward(self.n, self.rows, _ptr(src_of), _ptr(gt), _ptr(gz), 1, _stream()))
+                gt = gz
+            self.ws.zero_()
+        self._src_version = -1      # an optimizer step follows (the fused one writes through raw pointers: no version bump)
+        if self.table.grad is None:
+            self.table.grad = gt
+        else:
+            self.table.grad.add_(gt)
+        return self.table.grad
+
+
 class _TableDistFn(torch.autograd.Function):
     """dist(table[idx[:,0]], table[idx[:,1]]) with the gather fused into the forward kernel and the
     gather backward (dense index_put in the reference, sympa/embeddings.py:29-34) fused into an
     atomic scatter-add."""
 
     @staticmethod
-    def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False, by_rows=None):
+    def forward(ctx, table, idx, wsum_w, kind, metric, sync_grad=False, by_rows=None, acc=None):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        ctx.acc = acc
+        if acc is not None:     # gradient accumulation over the calls of a step: see TableGradAccumulator
+            if acc.table is not table:
+                raise ValueError("the accumulator was made for another table")
+            dist, vvd, saved = forward_raw(acc.kind, metric, table=acc.source(), idx=idx, wsum_w=wsum_w, want_grad=need)
+            ctx.kind, ctx.metric, ctx.tshape, ctx.sync_grad, ctx.by_rows = acc.kind, metric, table.shape, False, False
+            ctx.save_for_backward(saved, vvd, idx, wsum_w if metric == "wsum" else None, None)
+            ctx.mark_non_differentiable(vvd)
+            return dist, vvd
         # bounded domain, batch covering the table densely: the inverse Cayley transform is applied once per
         # table row (sympa_bounded_rows_to_upper) and the pairs run the upper-half kernels on the result
         # (break-even in flops is 2 pairs per row)
@@ -242,6 +313,21 @@ class _TableDistFn(torch.autograd.Function):
         grad_dist = _require(grad_dist, "grad_dist")
         b, n = vvd.shape
         dev = vvd.device
+        if ctx.acc is not None:
+            acc = ctx.acc
+            gw = None
+            with torch.cuda.device(dev):
+                k, m = _lib.KIND[ctx.kind], _lib.METRIC[ctx.metric]
+                if b > 0:
+                    _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), acc.rows, _ptr(idx.contiguous()),
+                                                                _ptr(acc.ws), acc.nbytes, _stream()))
+                if wsum_w is not None and ctx.needs_input_grad[2]:
+                    gw = torch.zeros(n, dtype=torch.float64, device=dev)
+                    if b > 0:
+                        _lib.check(lib.sympa_dist_backward(k, n, m, b, _ptr(grad_dist), _ptr(saved), None, None, None, 0, None,
+                                                           _ptr(vvd), _ptr(wsum_w.contiguous().reshape(-1)), _ptr(gw), _stream()))
+                    gw = gw.reshape(wsum_w.shape)
+            return None, None, gw, None, None, None, None, None      # the table gradient arrives with acc.finish()
         with torch.cuda.device(dev):
             # every decision below depends on (kind, n, rows, sync_grad) only, never on the local batch: with
             # sync_grad all ranks must enter the same collectives on buffers of the same size, a rank with an
@@ -304,7 +390,7 @@ class _TableDistFn(torch.autograd.Function):
                 gt = gz
         if gw is not None:
             gw = gw.reshape(wsum_w.shape)
-        return gt, None, gw, None, None, None, None
+        return gt, None, gw, None, None, None, None, None
 
 
 def dist(kind, metric, z1, z2, wsum_w=None):
@@ -339,12 +425,14 @@ def _allreduce_avg(t, async_op=False):
     return None
 
 
-def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False, by_rows=None):
+def table_dist(kind, metric, table, idx, wsum_w=None, sync_grad=False, by_rows=None, accumulator=None):
     """sync_grad=True: the backward also averages the table gradient (and dL/dw of wsum) over the ranks of
     the default process group - on the packed gradient table where there is one - so the caller must NOT
     all-reduce table.grad again.  Every rank of the group must make the call (an empty local batch included).
     by_rows: force / forbid the bounded-domain row route (None: bounded_by_rows decides)."""
-    return _TableDistFn.apply(table, idx, wsum_w, kind, metric, bool(sync_grad), by_rows)
+    if accumulator is not None and sync_grad:
+        raise ValueError("with an accumulator the collective runs in accumulator.finish(sync_grad=True)")
+    return _TableDistFn.apply(table, idx, wsum_w, kind, metric, bool(sync_grad), by_rows, accumulator)
 
 
 def distortion_step(kind, metric, table, idx, graph_dist, scale, grad_table, wsum_w=None, grad_wsum_w=None,

@@ -734,3 +734,71 @@ def test_table_grad_scatter_rows_equals_full_scatter(sb, kind, n):
     assert lib.sympa_table_grad_scatter_rows(k, n, pairs, gdist.data_ptr(), saved.data_ptr(), rows, idx.data_ptr(), 5, rows + 1,
                                              parts.data_ptr(), need, stream) == 1      # range outside the table
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n,metric", [("upper", 4, "riem"), ("bounded", 3, "fone"), ("upper", 10, "wsum"), ("spd", 5, "riem"),
+                                           ("bounded", 8, "fmin")])
+def test_table_grad_accumulator_equals_one_call(sb, kind, n, metric):
+    """Gradient accumulation over the chunks of a step (TableGradAccumulator, runner.py:104 grad_accum_steps): three
+    dist_from_table calls sharing an accumulator + finish() give the table gradient (and dL/dw) of one call on the
+    whole batch, and the oracle's; a second step starts from a clean accumulator; the cached transformed table of
+    the bounded domain follows in-place updates of the table."""
+    g = torch.Generator().manual_seed(77 + n)
+    rows, b = 41, 300
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g)
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+    src = torch.randint(0, rows, (b,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1)
+    gdist = torch.randint(1, 20, (b,), generator=g).double()
+    w = torch.linspace(-0.2, 1.1, n, dtype=torch.float64).reshape(1, n) if metric == "wsum" else None
+    man = (sb.SymmetricPositiveDefinite().cuda() if kind == "spd" else make_manifold(sb, kind, n, metric, None if w is None else w.numpy()))
+    idx_c, gd_c = idx.cuda(), gdist.cuda()
+
+    def one_call(t):
+        d = man.dist_from_table(t, idx_c)
+        so.distortion_loss(gd_c, d).backward()
+
+    ref = table.cuda().requires_grad_(True)
+    one_call(ref)
+    gw_ref = None if w is None else man.metric.weights.grad.clone()
+    if w is not None:
+        man.metric.weights.grad = None
+
+    t = table.cuda().requires_grad_(True)
+    acc = man.table_grad_accumulator(t)
+    for step in range(2):
+        t.grad = None
+        for lo, hi in ((0, 100), (100, 101), (101, b)):
+            d = man.dist_from_table(t, idx_c[lo:hi], accumulator=acc)
+            so.distortion_loss(gd_c[lo:hi], d).backward()
+        assert t.grad is None                      # nothing dense until the step is finished
+        acc.finish()
+        torch.testing.assert_close(t.grad, ref.grad, rtol=1e-11, atol=1e-12 * ref.grad.abs().max().item())
+        if w is not None:
+            torch.testing.assert_close(man.metric.weights.grad, gw_ref, rtol=1e-11, atol=1e-13)
+            man.metric.weights.grad = None
+    # against the oracle
+    to = table.clone().requires_grad_(True)
+    wo = None if w is None else w.clone().requires_grad_(True)
+    so.distortion_loss(gdist, so.dist(kind, to[idx[:, 0]], to[idx[:, 1]], metric, wo)).backward()
+    go = so.sym(to.grad)
+    assert (t.grad.cpu() - go).abs().max().item() <= grad_tolerance(n) * go.abs().max().item()
+    # finish() accumulates into an existing gradient
+    before = t.grad.clone()
+    d = man.dist_from_table(t, idx_c, accumulator=acc)
+    so.distortion_loss(gd_c, d).backward()
+    acc.finish()
+    torch.testing.assert_close(t.grad, 2 * before, rtol=1e-11, atol=1e-12 * before.abs().max().item())
+    # in-place update of the table (an optimizer step): the next step must see the new points
+    with torch.no_grad():
+        t.copy_(torch.roll(t, 1, 0))
+    t.grad = None
+    d_new = man.dist_from_table(t, idx_c, accumulator=acc)
+    torch.testing.assert_close(d_new.detach(), man.dist_from_table(t.detach(), idx_c), rtol=1e-13, atol=1e-15)
+    assert not torch.allclose(d_new.detach(), d.detach())
+    sb.ops.check_status()

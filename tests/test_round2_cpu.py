@@ -87,5 +87,5 @@ def test_bounded_route_choice_is_rank_invariant_under_sync_grad():
         mp.spawn(_route_worker, args=(world, port, out), nprocs=world, join=True)
         r0, r1 = out[0], out[1]
     assert all(same for same, _ in r0[0]) and all(same for same, _ in r1[0])
-    assert [v for _, v in r0[0]] == [True, True, False, False]
+    assert [v for _, v in r0[0]] == [True, True, True, False]      # bounded by rows up to n = 10 (ops.BOUNDED_BY_ROWS_MAX_N)
     assert (r0[1], r1[1]) == (True, False)       # single-process rule: 2 * pairs >= rows
