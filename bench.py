@@ -34,6 +34,8 @@ N10_GLOBAL_PAIRS = 1 << 23      # batch of the n = 10 side record (a step is ~0.
 
 
 def chunk_pairs_for(n):
+    if os.environ.get("SYMPA_BENCH_CHUNK_LOG2"):          # (experiments)
+        return 1 << int(os.environ["SYMPA_BENCH_CHUNK_LOG2"])
     return CHUNK_PAIRS if n <= 4 else ((1 << 21) if n <= 6 else (1 << 19))
 
 

@@ -177,10 +177,14 @@ int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* wor
 /* The scatter half WITHOUT the zeroing: adds the batch's contributions to a packed gradient table the caller keeps
  * across several batches of one step (gradient accumulation, runner.py:104: grad_accum_steps) - the caller zeroes the
  * workspace at the start of the step, calls this once per batch, then [all-reduces and] expands once per step.
- * (dL/dw of the wsum metric: sympa_dist_backward with only grad_wsum_w.) */
+ * (dL/dw of the wsum metric: sympa_dist_backward with only grad_wsum_w.)
+ * max_sms > 0 with tickets != NULL (8 bytes of device memory, contents irrelevant, owned by the call until it has
+ * run): the scatter confines itself to the SMs with id < max_sms, so that a caller who issues it on a side stream
+ * leaves the other SMs to the forward kernel of the next batch (the two kernels cannot share an SM); max_sms = 0:
+ * the whole GPU. */
 int sympa_table_grad_scatter_add(int kind, int n, int64_t num_pairs, const double* grad_dist, const double* saved_state,
                                  int64_t num_rows, const int64_t* idx, double* workspace, int64_t workspace_bytes,
-                                 void* stream);
+                                 int max_sms, unsigned int* tickets, void* stream);
 /* The scatter half restricted to the destination rows [row_begin, row_end): zeroes that range of the packed
  * workspace and scatter-adds the batch's contributions to it (dL/dw of the wsum metric is NOT computed here:
  * use sympa_dist_backward with only grad_wsum_w).  Lets a data-parallel caller pipeline the collective: scatter

@@ -96,7 +96,7 @@ def load():
     lib.sympa_table_grad_scatter_rows.restype = I
     lib.sympa_table_grad_scatter_rows.argtypes = [I, I, L, P, P, L, P, L, L, P, L, P]
     lib.sympa_table_grad_scatter_add.restype = I
-    lib.sympa_table_grad_scatter_add.argtypes = [I, I, L, P, P, L, P, P, L, P]
+    lib.sympa_table_grad_scatter_add.argtypes = [I, I, L, P, P, L, P, P, L, I, P, P]
     lib.sympa_table_grad_expand.restype = I
     lib.sympa_table_grad_expand.argtypes = [I, I, L, P, P, I, P]
     lib.sympa_distortion_loss_forward.restype = I

@@ -502,7 +502,10 @@ static int launch_split(const PairArgs& a, double* scratch, int64_t cap, cudaStr
 template <int N, int KIND, int MODE>
 static int launch_coop(const PairArgs& a, cudaStream_t s) {
   constexpr int PW = CoopCfg<N>::PW;
-  constexpr int smem = PW * CoopTraits<N, KIND>::kDoubles * (int)sizeof(double);
+#ifndef SY_COOP_SMEM_PAD
+#define SY_COOP_SMEM_PAD 0   // experiment: unused shared memory per CTA, to lower the number of resident CTAs
+#endif
+  constexpr int smem = PW * CoopTraits<N, KIND>::kDoubles * (int)sizeof(double) + SY_COOP_SMEM_PAD;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(coop_kernel<N, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

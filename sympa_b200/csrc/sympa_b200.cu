@@ -141,6 +141,134 @@ __global__ void __launch_bounds__(256) scatter_packed_table_kernel(int64_t total
   }
 }
 
+// The same scatter over ALL destination rows (the default: one pass), written for memory-level parallelism: ncu
+// showed the ranged kernel above latency-bound at full occupancy (long_scoreboard 44 per issue, DRAM at 60 % of
+// its peak) - every work item was one dependent chain index -> range test -> state loads -> atomics.  Here the
+// state of both operands does not wait for the indices, and U work items per thread are loaded before the first
+// atomic is issued.  T is the work-item counter type (32-bit when total < 2^31: the division by per_s is a
+// fifth of the 64-bit one).
+template <int U, typename T>
+__global__ void __launch_bounds__(256) scatter_packed_all_kernel(T total, int per_s, int64_t num_rows,
+                                                                 const double* __restrict__ gd,
+                                                                 const int64_t* __restrict__ idx,
+                                                                 const double* __restrict__ u1,
+                                                                 const double* __restrict__ u2, double* __restrict__ ws) {
+  const T stride = (T)gridDim.x * (T)blockDim.x;
+  const T first = (T)blockIdx.x * (T)blockDim.x + (T)threadIdx.x;
+  // the stride of 64-bit counters cannot overflow; 32-bit ones are only used when total + U * stride < 2^32
+  for (T e0 = first; e0 < total; e0 += (T)U * stride) {
+    double a1[U], a2[U], g[U];
+    int64_t i1[U], i2[U];
+    int c[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const T e = e0 + (T)k * stride;
+      const bool live = e < total;
+      const T ee = live ? e : first;     // (in range: first < total here)
+      const T p = ee / (T)per_s;
+      c[k] = (int)(ee - p * (T)per_s);
+      a1[k] = __ldg(u1 + ee);
+      a2[k] = __ldg(u2 + ee);
+      g[k] = __ldg(gd + p);
+      i1[k] = __ldg(idx + 2 * (int64_t)p);
+      i2[k] = __ldg(idx + 2 * (int64_t)p + 1);
+      if (!live) i1[k] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (i1[k] < 0 || i1[k] >= num_rows || i2[k] < 0 || i2[k] >= num_rows) continue;
+      atomicAdd(ws + i1[k] * per_s + c[k], g[k] * a1[k]);
+      atomicAdd(ws + i2[k] * per_s + c[k], g[k] * a2[k]);
+    }
+  }
+}
+
+#ifndef SY_SCATTER_UNROLL
+#define SY_SCATTER_UNROLL 4
+#endif
+
+// The same scatter confined to the SMs with %smid < sm_limit, for a caller that runs it on a side stream NEXT TO
+// the forward kernel of the following chunk (ops.TableGradAccumulator): the scatter is bound by L2 atomics and
+// DRAM read-modify-writes and leaves the FP64 pipes idle, the pair kernels are the opposite - but the two cannot
+// share an SM (two 128-thread pair CTAs own the whole register file), so the overlap is by SM partition.  The grid
+// is one full wave (8 CTAs of 256 threads per SM); CTAs that find themselves on another SM leave at once - freeing
+// it for the pair kernel - and the others pull chunks of work items from a ticket counter.  Wherever the CTAs
+// land the result is complete: the last CTA to leave drains the tickets that nobody took (in the worst case, no
+// CTA on a chosen SM, it does all the work alone - slow, never wrong).  tickets[0] = next chunk, tickets[1] = CTAs
+// that have left; both zeroed by the launcher on the same stream.
+// Work items are walked without divisions: a ticket is 256 PAIRS (256 * per_s items, contiguous in the saved
+// state); thread t takes the items t, t + 256, ... of the chunk, so its (pair, element) position advances by the
+// constant (256 / per_s, 256 % per_s) - the partition is bound by instruction issue per SM (one item per clock and SM
+// with the generic indexing of the kernels above), and every instruction saved is SM time given back to the pair kernel.
+template <int U>
+__global__ void __launch_bounds__(256) scatter_packed_part_kernel(int64_t num_pairs, int per_s, int64_t num_rows, int sm_limit,
+                                                                  unsigned int* __restrict__ tickets,
+                                                                  const double* __restrict__ gd,
+                                                                  const int64_t* __restrict__ idx,
+                                                                  const double* __restrict__ u1,
+                                                                  const double* __restrict__ u2, double* __restrict__ ws) {
+  __shared__ unsigned int s_ticket;
+  __shared__ int s_last;
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  bool work = (int)smid < sm_limit, drain = false;
+  const int t = threadIdx.x;
+  const int p_first = t / per_s, c_first = t - p_first * per_s;
+  const int step_p = 256 / per_s, step_c = 256 - step_p * per_s;
+  const longlong2* __restrict__ idx2 = reinterpret_cast<const longlong2*>(idx);
+  for (;;) {
+    if (work) {
+      for (;;) {
+        if (t == 0) s_ticket = atomicAdd(tickets, 1u);
+        __syncthreads();
+        const int64_t pair0 = (int64_t)s_ticket * 256;
+        __syncthreads();
+        if (pair0 >= num_pairs) break;
+        const int left = (num_pairs - pair0) < 256 ? (int)(num_pairs - pair0) : 256;   // pairs of this chunk
+        const double* __restrict__ v1 = u1 + pair0 * per_s + t;
+        const double* __restrict__ v2 = u2 + pair0 * per_s + t;
+        int pl = p_first, c = c_first;
+#pragma unroll 1
+        for (int i0 = 0; i0 < per_s; i0 += U) {
+          double a1[U], a2[U], g[U];
+          longlong2 ij[U];
+          int cc[U];
+#pragma unroll
+          for (int k = 0; k < U; ++k) {
+            const bool live = i0 + k < per_s && pl < left;
+            const int off = live ? (i0 + k) * 256 : 0;
+            const int64_t pp = pair0 + (live ? pl : 0);
+            a1[k] = __ldg(v1 + off);
+            a2[k] = __ldg(v2 + off);
+            g[k] = __ldg(gd + pp);
+            ij[k] = __ldg(idx2 + pp);
+            if (!live) ij[k].x = -1;
+            cc[k] = c;
+            pl += step_p;
+            c += step_c;
+            if (c >= per_s) {
+              c -= per_s;
+              ++pl;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < U; ++k) {
+            if (ij[k].x < 0 || ij[k].x >= num_rows || ij[k].y < 0 || ij[k].y >= num_rows) continue;
+            atomicAdd(ws + ij[k].x * per_s + cc[k], g[k] * a1[k]);
+            atomicAdd(ws + ij[k].y * per_s + cc[k], g[k] * a2[k]);
+          }
+        }
+      }
+    }
+    if (drain) return;
+    // leaving: the last CTA of the grid to get here checks that every ticket was taken
+    if (t == 0) s_last = (atomicAdd(tickets + 1, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last || work) return;   // a working CTA only leaves when the tickets are exhausted: nothing to drain
+    work = drain = true;           // the last CTA sat on an SM outside the partition: drain (normally nothing is left)
+  }
+}
+
 __global__ void __launch_bounds__(256) expand_table_kernel(int64_t total, int per, int per_s, int n, int overwrite,
                                                            const double* __restrict__ ws, double* __restrict__ grad_table) {
   __shared__ short lut[2 * SYMPA_MAX_N * SYMPA_MAX_N];
@@ -362,11 +490,19 @@ static int64_t g_scatter_pass_bytes = 1ll << 46;
 // scatter-add of a batch into the rows [row_begin, row_end) of the packed gradient table, in L2-sized passes
 static int launch_packed_scatter(int64_t num_pairs, int per_s, int64_t num_rows, const double* grad_dist, const int64_t* idx,
                                  const double* u1, const double* u2, double* workspace, cudaStream_t s,
-                                 int64_t row_begin = 0, int64_t row_end = -1) {
+                                 int64_t row_begin = 0, int64_t row_end = -1, int max_sms = 0, unsigned int* tickets = nullptr) {
   if (row_end < 0) row_end = num_rows;
   const int64_t span = row_end - row_begin;
   if (span <= 0) return SYMPA_OK;
   const int64_t total = num_pairs * (int64_t)per_s;
+  if (max_sms > 0 && tickets != nullptr && row_begin == 0 && row_end == num_rows) {   // SM-partitioned, for overlap
+    constexpr int U = SY_SCATTER_UNROLL;
+    const int grid = grid_for((int64_t)1 << 40, 256, 8);      // one full wave: 8 CTAs of 256 threads on every SM
+    if (cudaMemsetAsync(tickets, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) return check_launch();
+    // (tickets: at most num_pairs / 256 + grid + 1 < 2^32 for any batch that fits the memory)
+    scatter_packed_part_kernel<U><<<grid, 256, 0, s>>>(num_pairs, per_s, num_rows, max_sms, tickets, grad_dist, idx, u1, u2, workspace);
+    return check_launch();
+  }
   const int64_t table_bytes = span * (int64_t)per_s * (int64_t)sizeof(double);
   int64_t passes = (table_bytes + g_scatter_pass_bytes - 1) / g_scatter_pass_bytes;
   // a pass costs a sweep over the indices of all pairs: no more passes than the batch can pay for
@@ -374,6 +510,16 @@ static int launch_packed_scatter(int64_t num_pairs, int per_s, int64_t num_rows,
   if (passes > max_passes) passes = max_passes;
   if (passes > 16) passes = 16;
   if (passes < 1) passes = 1;
+  if (passes == 1 && row_begin == 0 && row_end == num_rows) {
+    constexpr int U = SY_SCATTER_UNROLL;
+    const int grid = grid_for((total + U - 1) / U, 256, 32);
+    if (total + (int64_t)(U + 1) * grid * 256 < (1ll << 32))
+      scatter_packed_all_kernel<U, unsigned int><<<grid, 256, 0, s>>>((unsigned int)total, per_s, num_rows, grad_dist, idx, u1, u2,
+                                                                     workspace);
+    else
+      scatter_packed_all_kernel<U, int64_t><<<grid, 256, 0, s>>>(total, per_s, num_rows, grad_dist, idx, u1, u2, workspace);
+    return check_launch();
+  }
   const int64_t rows_per_pass = (span + passes - 1) / passes;
   for (int64_t lo = row_begin; lo < row_end; lo += rows_per_pass) {
     const int64_t hi = lo + rows_per_pass < row_end ? lo + rows_per_pass : row_end;
@@ -740,7 +886,8 @@ int sympa_table_grad_scatter_rows(int kind, int n, int64_t num_pairs, const doub
 }
 
 int sympa_table_grad_scatter_add(int kind, int n, int64_t num_pairs, const double* grad_dist, const double* saved_state,
-                                 int64_t num_rows, const int64_t* idx, double* workspace, int64_t workspace_bytes, void* stream) {
+                                 int64_t num_rows, const int64_t* idx, double* workspace, int64_t workspace_bytes, int max_sms,
+                                 unsigned int* tickets, void* stream) {
   if (!valid_common(kind, n, 0, num_pairs)) return (n < 1 || n > SYMPA_MAX_N) ? SYMPA_ERR_UNSUPPORTED : SYMPA_ERR_BAD_ARG;
   if (num_rows <= 0) return SYMPA_ERR_BAD_ARG;
   const int64_t need = sympa_backward_workspace_bytes(kind, n, num_rows);
@@ -749,7 +896,7 @@ int sympa_table_grad_scatter_add(int kind, int n, int64_t num_pairs, const doubl
   if (grad_dist == nullptr || saved_state == nullptr || idx == nullptr) return SYMPA_ERR_BAD_ARG;
   const int per_s = state_doubles(kind, n);
   return launch_packed_scatter(num_pairs, per_s, num_rows, grad_dist, idx, saved_state, saved_state + num_pairs * (int64_t)per_s,
-                               workspace, (cudaStream_t)stream);
+                               workspace, (cudaStream_t)stream, 0, -1, max_sms, tickets);
 }
 
 int sympa_table_grad_expand(int kind, int n, int64_t num_rows, const double* workspace, double* grad_table, int overwrite,

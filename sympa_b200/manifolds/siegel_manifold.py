@@ -63,9 +63,9 @@ class SiegelManifold(Manifold, ABC):
                               accumulator=accumulator)
         return d
 
-    def table_grad_accumulator(self, table: torch.Tensor):
+    def table_grad_accumulator(self, table: torch.Tensor, scatter_sms=None):
         """see sympa_b200.ops.TableGradAccumulator"""
-        return ops.TableGradAccumulator(self.kind, table)
+        return ops.TableGradAccumulator(self.kind, table, scatter_sms)
 
     def dist_matrix(self, table: torch.Tensor, row_begin: int = 0, row_count=None) -> torch.Tensor:
         """All-pairs distances between the rows of `table` (rows [row_begin, row_begin + row_count) of the

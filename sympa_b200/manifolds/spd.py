@@ -38,9 +38,9 @@ class SymmetricPositiveDefinite(Manifold):
         d, _ = ops.table_dist("spd", "riem", table, idx, sync_grad=sync_grad, accumulator=accumulator)
         return d
 
-    def table_grad_accumulator(self, table):
+    def table_grad_accumulator(self, table, scatter_sms=None):
         """see sympa_b200.ops.TableGradAccumulator"""
-        return ops.TableGradAccumulator("spd", table)
+        return ops.TableGradAccumulator("spd", table, scatter_sms)
 
     def dist_matrix(self, table, row_begin=0, row_count=None):
         """all-pairs distances between the rows of `table` (see SiegelManifold.dist_matrix)"""

@@ -3,6 +3,8 @@
 PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic of
 `dist` happens in libsympa_b200.so.  Tensors must be CUDA float64 and contiguous.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -204,6 +206,11 @@ def bounded_by_rows(kind, n, num_pairs, num_rows, sync_grad):
     return 2 * num_pairs >= num_rows
 
 
+# SMs the scatter of an accumulated chunk confines itself to while it runs on the accumulator's side stream next to
+# the forward kernel of the following chunk (0: no overlap, the scatter runs on the caller's stream on all SMs)
+ACC_SCATTER_SMS = int(os.environ.get("SYMPA_ACC_SCATTER_SMS", "48"))
+
+
 class TableGradAccumulator:
     """Gradient accumulation over the dist_from_table calls of ONE step (the reference's grad_accum_steps,
     runner.py:104): the backward of every call scatter-adds into one packed gradient table, and finish() - once
@@ -219,8 +226,15 @@ class TableGradAccumulator:
         acc.finish(sync_grad=world_size > 1)       # table.grad is ready (accumulated into if it already existed)
     """
 
-    def __init__(self, kind, table):
+    def __init__(self, kind, table, scatter_sms=None):
         lib = _lib.load()
+        # the scatter of a chunk is bound by L2 atomics / DRAM and the forward kernel of the next chunk by the FP64
+        # pipes: the scatter goes to a high-priority side stream and keeps to `scatter_sms` SMs (the two kernels
+        # cannot share an SM: the pair kernel's two CTAs own the register file), finish() joins the streams
+        self.scatter_sms = ACC_SCATTER_SMS if scatter_sms is None else int(scatter_sms)
+        self.stream = torch.cuda.Stream(device=table.device, priority=-1) if self.scatter_sms > 0 else None
+        self.tickets = torch.zeros(4, dtype=torch.int32, device=table.device)
+        self._pending = False
         self.table = table
         self.n, self.rows = table.shape[-1], table.shape[0]
         _check_n(self.n)
@@ -244,9 +258,29 @@ class TableGradAccumulator:
             self._src, self._src_of, self._src_version = src, t, self.table._version
         return self._src
 
+    def scatter_add(self, kind, n, b, grad_dist, saved, idx):
+        """this chunk's contribution into the packed table (called by the backward of dist_from_table)"""
+        lib = _lib.load()
+        k = _lib.KIND[kind]
+        if self.stream is None:
+            _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), self.rows, _ptr(idx), _ptr(self.ws),
+                                                        self.nbytes, 0, None, _stream()))
+            return
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)            # grad_dist and the saved state are ready, the table zeroed
+        with torch.cuda.stream(self.stream):
+            _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), self.rows, _ptr(idx), _ptr(self.ws),
+                                                        self.nbytes, self.scatter_sms, _ptr(self.tickets), self.stream.cuda_stream))
+        for t in (grad_dist, saved, idx):       # allocated on the caller's stream, last used on the side stream
+            t.record_stream(self.stream)
+        self._pending = True
+
     def finish(self, sync_grad=False):
         lib = _lib.load()
         dev = self.table.device
+        if self._pending:
+            torch.cuda.current_stream(dev).wait_stream(self.stream)
+            self._pending = False
         with torch.cuda.device(dev):
             if sync_grad:
                 _allreduce_avg(self.ws)
@@ -319,8 +353,7 @@ class _TableDistFn(torch.autograd.Function):
             with torch.cuda.device(dev):
                 k, m = _lib.KIND[ctx.kind], _lib.METRIC[ctx.metric]
                 if b > 0:
-                    _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), acc.rows, _ptr(idx.contiguous()),
-                                                                _ptr(acc.ws), acc.nbytes, _stream()))
+                    acc.scatter_add(ctx.kind, n, b, grad_dist, saved, idx.contiguous())
                 if wsum_w is not None and ctx.needs_input_grad[2]:
                     gw = torch.zeros(n, dtype=torch.float64, device=dev)
                     if b > 0:

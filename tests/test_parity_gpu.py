@@ -802,3 +802,29 @@ def test_table_grad_accumulator_equals_one_call(sb, kind, n, metric):
     torch.testing.assert_close(d_new.detach(), man.dist_from_table(t.detach(), idx_c), rtol=1e-13, atol=1e-15)
     assert not torch.allclose(d_new.detach(), d.detach())
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("scatter_sms", [0, 1, 48, 1 << 20])
+def test_accumulator_scatter_on_side_stream_sm_partition(sb, scatter_sms):
+    """The accumulator's scatter on its side stream, confined to `scatter_sms` SMs (ticket-pulled work, last CTA
+    drains): every work item exactly once wherever the CTAs land - 1 SM, a partition, more SMs than there are -
+    and the streams joined by finish().  Against one call on the whole batch."""
+    n, rows, b = 4, 3000, 200_000
+    g = torch.Generator().manual_seed(5)
+    table = so.upper_spread(rows, n, generator=g, scale=0.3).cuda()
+    src = torch.randint(0, rows, (b,), generator=g)
+    dst = (src + 1 + torch.randint(0, rows - 1, (b,), generator=g)) % rows
+    idx = torch.stack((src, dst), 1).cuda()
+    gd = torch.randint(1, 20, (b,), generator=g).double().cuda()
+    man = make_manifold(sb, "upper", n, "riem")
+    ref = table.clone().requires_grad_(True)
+    so.distortion_loss(gd, man.dist_from_table(ref, idx)).backward()
+    t = table.clone().requires_grad_(True)
+    acc = man.table_grad_accumulator(t, scatter_sms=scatter_sms)
+    for step in range(2):
+        t.grad = None
+        for lo, hi in ((0, 70_000), (70_000, 70_001), (70_001, b)):
+            so.distortion_loss(gd[lo:hi], man.dist_from_table(t, idx[lo:hi], accumulator=acc)).backward()
+        acc.finish()
+        torch.testing.assert_close(t.grad, ref.grad, rtol=1e-10, atol=1e-12 * ref.grad.abs().max().item())
+    sb.ops.check_status()
