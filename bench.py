@@ -248,6 +248,8 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
         total = torch.zeros((), dtype=torch.float64, device=dev)
         for c in range(n_chunks):
             idx_c, gd_c = get_chunk(c)
+            if acc is not None and c == n_chunks - 1:
+                acc.last_chunk()         # its scatter has no forward kernel to overlap with: whole GPU
             d = man.dist_from_table(table, idx_c, sync_grad=(world > 1 and acc is None), accumulator=acc)
             loss = loss_fn.calculate_loss(gd_c, d * scale)
             loss.backward()
@@ -551,6 +553,9 @@ def run_ours(args):
     rank, world, local = sd.init_process_group()
     assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
     dev = torch.device("cuda", local)
+    # pinned host buffers NUMA-local to this rank's GPU (SYMPA_BENCH_NO_NUMA=1 switches it off for an A/B)
+    # - only with several ranks: one rank keeps every host core for the CPU baseline it also times
+    numa = None if (os.environ.get("SYMPA_BENCH_NO_NUMA") or world == 1) else sd.bind_to_gpu_numa_node(local)
     if os.environ.get("SYMPA_SCATTER_PASS_MB"):     # tuning experiments only
         from sympa_b200 import _lib
         _lib.check(_lib.load().sympa_set_option(_lib.OPT_SCATTER_PASS_MB, int(os.environ["SYMPA_SCATTER_PASS_MB"])))
@@ -577,7 +582,9 @@ def run_ours(args):
                    "chunk_pairs": res["chunk_pairs"], "rows": rows, "n": n, "kind": kind, "metric": args.metric,
                    "l2": "table (268 MB at n=4) + saved unit gradients + indices of a chunk exceed the 126 MB L2 many times "
                          "over (no explicit flush needed)",
-                   "parallelism": par},
+                   "parallelism": par,
+                   "host_numa": (f"rank 0 runs on the {numa['cpus']} CPUs of NUMA node {numa['node']} (its GPU's node): pinned "
+                                 "buffers are first-touched there" if numa else "not bound (topology unreadable or switched off)")},
         "e2e": res["e2e"],
         "gpu_launches": res["gpu_launches"],
         "gpu_launches_how": f"{res['launches_per_chunk']} kernels of libsympa_b200.so per chunk x {res['chunks_per_step']} "

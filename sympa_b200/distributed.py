@@ -27,6 +27,42 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index=None):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off (Linux sysfs), so that the pinned host
+    buffers it allocates afterwards are first-touched there: with one process per GPU on a two-socket box the
+    ranks on the far socket otherwise read their batches across the inter-socket link.  Returns
+    {"node": k, "cpus": count} or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        if not torch.cuda.is_available():
+            return None
+        index = torch.cuda.current_device() if device_index is None else int(device_index)
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)        # never widen what the launcher (cgroup, taskset) allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def shard_indices(num_items, rank, world, epoch=0, shuffle=True, seed=0, drop_last=False, device=None):
     """Same partition as torch.utils.data.DistributedSampler(num_replicas=world, rank=rank)
     (train.py:108): a seeded permutation, padded by wrapping so every rank gets ceil(T / world)

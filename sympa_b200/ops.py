@@ -231,10 +231,14 @@ class TableGradAccumulator:
         # the scatter of a chunk is bound by L2 atomics / DRAM and the forward kernel of the next chunk by the FP64
         # pipes: the scatter goes to a high-priority side stream and keeps to `scatter_sms` SMs (the two kernels
         # cannot share an SM: the pair kernel's two CTAs own the register file), finish() joins the streams
-        self.scatter_sms = ACC_SCATTER_SMS if scatter_sms is None else int(scatter_sms)
+        # (n = 2 is bound by HBM, not by the FP64 pipes: its forward kernel is shorter than a scatter on a third of
+        # the SMs, measured 8.9 -> 7.5 G pairs/s with the partition - no overlap there unless asked for)
+        self.scatter_sms = (ACC_SCATTER_SMS if table.shape[-1] >= 3 else 0) if scatter_sms is None else int(scatter_sms)
         self.stream = torch.cuda.Stream(device=table.device, priority=-1) if self.scatter_sms > 0 else None
         self.tickets = torch.zeros(4, dtype=torch.int32, device=table.device)
         self._pending = False
+        self._hold = None
+        self._last = False
         self.table = table
         self.n, self.rows = table.shape[-1], table.shape[0]
         _check_n(self.n)
@@ -262,25 +266,41 @@ class TableGradAccumulator:
         """this chunk's contribution into the packed table (called by the backward of dist_from_table)"""
         lib = _lib.load()
         k = _lib.KIND[kind]
-        if self.stream is None:
+        cur = torch.cuda.current_stream()
+        self._join(cur)
+        if self.stream is None or self._last:      # nothing to overlap with: the whole GPU, on the caller's stream
             _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), self.rows, _ptr(idx), _ptr(self.ws),
                                                         self.nbytes, 0, None, _stream()))
             return
-        cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)            # grad_dist and the saved state are ready, the table zeroed
         with torch.cuda.stream(self.stream):
             _lib.check(lib.sympa_table_grad_scatter_add(k, n, b, _ptr(grad_dist), _ptr(saved), self.rows, _ptr(idx), _ptr(self.ws),
                                                         self.nbytes, self.scatter_sms, _ptr(self.tickets), self.stream.cuda_stream))
-        for t in (grad_dist, saved, idx):       # allocated on the caller's stream, last used on the side stream
-            t.record_stream(self.stream)
+        # The tensors the side stream reads belong to the caller's stream as far as the caching allocator knows.  They
+        # are kept alive here until the caller's stream has waited for the scatter (_join: at the next chunk's
+        # backward, by which time the scatter - overlapped with that chunk's forward - is over), so their memory
+        # is reused in stream order.  (tensor.record_stream instead would leave every chunk's 2.7 GB state
+        # unreusable for a host that enqueues many steps ahead: the allocator then grows until it has to
+        # synchronise and free - measured: 1.88 -> 1.50 G pairs/s over 25 steps.)
+        self._hold = (grad_dist, saved, idx)
         self._pending = True
+
+    def _join(self, cur):
+        if self._pending:
+            cur.wait_stream(self.stream)
+            self._pending = False
+        self._hold = None
+
+    def last_chunk(self):
+        """hint: the next backward is the last one before finish() - no forward kernel follows it, so its scatter
+        should use the whole GPU instead of the partition (optional; results do not depend on it)"""
+        self._last = True
 
     def finish(self, sync_grad=False):
         lib = _lib.load()
         dev = self.table.device
-        if self._pending:
-            torch.cuda.current_stream(dev).wait_stream(self.stream)
-            self._pending = False
+        self._last = False
+        self._join(torch.cuda.current_stream(dev))
         with torch.cuda.device(dev):
             if sync_grad:
                 _allreduce_avg(self.ws)

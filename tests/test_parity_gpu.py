@@ -824,7 +824,24 @@ def test_accumulator_scatter_on_side_stream_sm_partition(sb, scatter_sms):
     for step in range(2):
         t.grad = None
         for lo, hi in ((0, 70_000), (70_000, 70_001), (70_001, b)):
+            if step == 1 and hi == b:
+                acc.last_chunk()        # hint: whole GPU for the scatter that nothing follows
             so.distortion_loss(gd[lo:hi], man.dist_from_table(t, idx[lo:hi], accumulator=acc)).backward()
         acc.finish()
         torch.testing.assert_close(t.grad, ref.grad, rtol=1e-10, atol=1e-12 * ref.grad.abs().max().item())
+    # a host that enqueues many steps ahead of the device must not make the allocator grow (the state a side-stream
+    # scatter reads is held until the caller's stream has joined it, then reused in stream order)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    peaks = []
+    for step in range(12):
+        t.grad = None
+        for lo, hi in ((0, 70_000), (70_000, 140_000), (140_000, b)):
+            so.distortion_loss(gd[lo:hi], man.dist_from_table(t, idx[lo:hi], accumulator=acc)).backward()
+        acc.finish()
+        peaks.append(torch.cuda.max_memory_allocated() - base)
+    torch.cuda.synchronize()
+    assert peaks[-1] <= 1.05 * peaks[1], peaks
+    torch.testing.assert_close(t.grad, ref.grad, rtol=1e-10, atol=1e-12 * ref.grad.abs().max().item())
     sb.ops.check_status()
