@@ -310,7 +310,8 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
         ws, ws_bytes = ops.backward_workspace_for(kk, n, rows, dev)
         gt = torch.empty_like(table)
         stream = torch.cuda.current_stream().cuda_stream
-        for _ in range(min(steps, 10)):
+        torch.cuda.synchronize()
+        for it in range(min(steps, 10) + 1):      # (the first pass is a warm-up: its allocations can fall between the events)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
             if by_rows:
                 ev[4].record()
@@ -333,14 +334,17 @@ def measure(kind, n, metric, rows, global_pairs, steps, warmup, rank, world, loc
                 _lib.check(lib.sympa_bounded_rows_backward(n, rows, table.data_ptr(), gt.data_ptr(), gz.data_ptr(), 1, stream))
                 ev[7].record()
             torch.cuda.synchronize()
+            if it == 0:
+                del saved, dd, vv
+                continue
             fwd_ms.append(ev[0].elapsed_time(ev[1]))
             bwd_ms.append(ev[2].elapsed_time(ev[3]))
             if by_rows:
                 rows_ms.append(ev[4].elapsed_time(ev[5]) + ev[6].elapsed_time(ev[7]))
             del saved, dd, vv
         del gt
-        res["kernel_ms"] = statistics.mean(fwd_ms)
-        res["backward_ms"] = statistics.mean(bwd_ms)
+        res["kernel_ms"] = statistics.median(fwd_ms)
+        res["backward_ms"] = statistics.median(bwd_ms)
         res["kernel_pairs"] = cb
         res["kernel_kind"] = kk
         if by_rows:
