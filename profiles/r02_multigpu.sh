@@ -17,7 +17,7 @@ print('launches', d['gpu_launches'], d['gpu_launches_how'][:90])
 for k,v in d.get('also',{}).items(): print(' ', k, v)
 "
 # A/B: the same short run without the NUMA binding of the ranks
-for v in 0 1; do
+for v in 1; do
   SYMPA_BENCH_NO_NUMA=$v python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$v bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-n10 > gpurun_out/r02_numa${v}_n$N.json 2>> gpurun_out/r02_bench_n$N.err
   python -c "
 import json

@@ -5,6 +5,7 @@ tests/test_distributed_gloo.py).  Checks, on every rank:
   * pairs sharded over the ranks + the averaged NCCL all-reduce of the table gradient == the full-batch
     gradient of one GPU / world; the all-reduce issued inside the backward on the packed gradient table
     (dist_from_table(..., sync_grad=True)) gives the same gradient;
+  * the same through a TableGradAccumulator (three calls, one all-reduce in finish(sync_grad=True));
   * the owner-computes optimizer step (reduce-scatter, fused sympa_rsgd_step on the owned rows,
     all-gather) leaves every rank with the table of the replicated step."""
 import os
@@ -67,6 +68,19 @@ def main():
             sd.allreduce_gradients([t.grad], average=True)
         grads.append(t.grad.clone())
     torch.testing.assert_close(grads[1], grads[0], rtol=1e-10, atol=1e-12 * grads[0].abs().max().item())
+
+    # gradient accumulation: the shard in three calls into one packed table (scatter on the accumulator's side stream),
+    # one all-reduce of the packed table in finish() - upper and bounded (by rows)
+    for m, tb, want in ((man, table, avg), (bman, btable, grads[0])):
+        t = tb.clone().requires_grad_(True)
+        acc = m.table_grad_accumulator(t)
+        cuts = [0, len(shard) // 2, len(shard) // 2 + 1, len(shard)]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sel = shard[lo:hi]
+            d = m.dist_from_table(t, idx[sel].contiguous(), accumulator=acc)
+            (torch.abs((d / gd[sel]) ** 2 - 1)).sum().backward()
+        acc.finish(sync_grad=True)
+        torch.testing.assert_close(t.grad, want, rtol=1e-10, atol=1e-12 * want.abs().max().item())
 
     lr = 0.05
     rep = table.clone()
