@@ -17,20 +17,29 @@ struct WarpExec {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p && active) != 0; }
 
-  // Register-resident one-sided Jacobi, Brent-Luk ring ordering (see jacobi_ring_host for the schedule):
-  // each lane keeps a top and a bottom column in registers; after every round the top row moves one
-  // lane up and the bottom row one lane down with two warp shuffles per value.  Every lane of the
-  // warp executes the shuffles (inactive lanes carry garbage that nobody reads).
-  // (Round 2 tried the exchange through shared memory instead - the pair's two G buffers are free while the
-  // columns live in registers; STS.128 / LDS.128 into per-lane slots, ~110 instructions per round against ~290
-  // for the shuffles and their selects - and measured it SLOWER: n = 10 13.6 ms against 11.2 ms per 2^19 pairs,
-  // n = 8 6.4 against 5.2 ms.  Two __syncwarp() and a store -> load round trip per round cost more at 1.25 warps
-  // per scheduler than the shuffles, which pipeline.)
+  // Register-resident one-sided Jacobi: each lane keeps two columns in registers, rotates them, and between two
+  // rounds passes ONE of them to its right neighbour in the group's ring (one-directional ring ordering).  Which one -
+  // the column it has just received (bit 1) or the one it kept (bit 0) - is a fixed schedule per (round, lane) found
+  // by exhaustive search (ring_send_masks): N - 1 rounds in which every pair of columns meets exactly once, from
+  // any starting arrangement, so sweep after sweep runs the same code.  Every lane of the warp executes the shuffles
+  // (inactive lanes carry garbage that nobody reads).
+  // Round 1 and most of round 2 used the Brent-Luk ordering here: two columns leave every lane per round (top row one
+  // lane up, bottom row one lane down) and the first / last lane of a group need selects on both: 4 SHFL + 6 FSEL
+  // per exchanged double against 2 SHFL + 4 SEL now - the exchange was 26 % of the instructions of the n = 10 kernel.
+  // Measured: n = 10 11.19 -> 10.95 ms per 2^19 pairs, n = 9 8.79 -> 8.72, n = 8 5.14 -> 5.12: two per cent - the rounds
+  // are bound by the latency of the dependent chain dots -> rotation parameters -> update at 1.25 warps per scheduler,
+  // not by the instructions of the exchange.
+  // (Round 2 also tried the Brent-Luk exchange through shared memory - STS.128 / LDS.128 into per-lane slots of the
+  // pair's idle G buffers, ~110 instructions per round - and measured it SLOWER: n = 10 13.6 ms against 11.2 ms per 2^19
+  // pairs: two __syncwarp() and a store -> load round trip per round cost more at 1.25 warps per scheduler than
+  // shuffles, which pipeline.)
   template <int N, bool IS_REAL>
   __device__ __forceinline__ int jacobi(double* gr, double* gi, double*) const {
     typedef coop::LayoutT<N, 2> L;
     constexpr int NP = L::NP, LD = L::LD, G = L::G;
     constexpr unsigned kFull = 0xffffffffu;
+    constexpr unsigned long long kSched = coop::ring_send_masks<G>();
+    const int src = (threadIdx.x & 31) - g + (g == 0 ? G - 1 : g - 1);   // left neighbour in the group's ring
     double tr[N], ti[N], br[N], bi[N];
     int tid = 2 * g, bid = 2 * g + 1;
 #pragma unroll
@@ -52,34 +61,27 @@ struct WarpExec {
       for (int r = 0; r < NP - 1; ++r) {
         if (!done) conv |= coop::rotate_columns<N, IS_REAL>(tr, ti, br, bi, &tn, &bn);
         if (G > 1) {
-          const bool first = g == 0, last = g == G - 1;
+          // bit r * G + g of the schedule: 1 = pass on the column received last (bottom), 0 = the kept one (top)
+          const bool pass_b = ((kSched >> (r * G + g)) & 1ull) != 0ull;
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            const double up_r = __shfl_up_sync(kFull, first ? br[i] : tr[i], 1);
-            const double dn_r = __shfl_down_sync(kFull, br[i], 1);
-            const double old_t = tr[i];
-            tr[i] = first ? old_t : up_r;
-            br[i] = last ? old_t : dn_r;
+            const double send_r = pass_b ? br[i] : tr[i];
+            tr[i] = pass_b ? tr[i] : br[i];
+            br[i] = __shfl_sync(kFull, send_r, src);
             if (!IS_REAL) {
-              const double up_i = __shfl_up_sync(kFull, first ? bi[i] : ti[i], 1);
-              const double dn_i = __shfl_down_sync(kFull, bi[i], 1);
-              const double old_ti = ti[i];
-              ti[i] = first ? old_ti : up_i;
-              bi[i] = last ? old_ti : dn_i;
+              const double send_i = pass_b ? bi[i] : ti[i];
+              ti[i] = pass_b ? ti[i] : bi[i];
+              bi[i] = __shfl_sync(kFull, send_i, src);
             }
           }
           {
-            const double up_n = __shfl_up_sync(kFull, first ? bn : tn, 1);
-            const double dn_n = __shfl_down_sync(kFull, bn, 1);
-            const double old_tn = tn;
-            tn = first ? old_tn : up_n;
-            bn = last ? old_tn : dn_n;
+            const double send_n = pass_b ? bn : tn;
+            tn = pass_b ? tn : bn;
+            bn = __shfl_sync(kFull, send_n, src);
           }
-          const int up_id = __shfl_up_sync(kFull, first ? bid : tid, 1);
-          const int dn_id = __shfl_down_sync(kFull, bid, 1);
-          const int old_tid = tid;
-          tid = first ? old_tid : up_id;
-          bid = last ? old_tid : dn_id;
+          const int send_id = pass_b ? bid : tid;
+          tid = pass_b ? tid : bid;
+          bid = __shfl_sync(kFull, send_id, src);
         }
       }
       // the flags are combined over the lanes of THIS pair's group only: a pair's sweep count, and

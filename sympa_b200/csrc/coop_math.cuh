@@ -46,6 +46,27 @@ struct LayoutT {
   static constexpr int kDoubles = (kRaw % 2 == 0) ? kRaw + 1 : kRaw;  // odd stride between pair slots
 };
 
+// One-directional ring ordering of the register-resident Jacobi (WarpExec::jacobi): G lanes hold two columns each;
+// after round r lane g sends one of them to lane (g + 1) mod G - bit g of mask r: 1 = the column it received after
+// the previous round, 0 = the one it kept - and keeps the other.  The masks below were found by exhaustive search
+// (every one of the N (N - 1) / 2 column pairs meets exactly once in the N - 1 = 2 G - 1 rounds of a sweep; the
+// schedule is positional, so it holds from any arrangement and the last mask, 0, starts the next sweep on pairs that
+// did not meet in the round before).  Packed: bit r * G + g.
+template <int G>
+SY_HD constexpr unsigned long long ring_send_masks() {
+  static_assert(G >= 1 && G <= 5, "schedules are tabulated for 2..10 columns");
+  constexpr unsigned m2[3] = {0, 1, 0};
+  constexpr unsigned m3[5] = {0, 3, 3, 6, 0};
+  constexpr unsigned m4[7] = {0, 7, 7, 14, 14, 13, 0};
+  constexpr unsigned m5[9] = {0, 15, 15, 30, 30, 29, 29, 27, 0};
+  unsigned long long packed = 0ull;
+  for (int r = 0; r < 2 * G - 1; ++r) {
+    const unsigned m = G == 2 ? m2[r < 3 ? r : 0] : (G == 3 ? m3[r < 5 ? r : 0] : (G == 4 ? m4[r < 7 ? r : 0] : (G == 5 ? m5[r < 9 ? r : 0] : 0u)));
+    packed |= (unsigned long long)m << (r * G);
+  }
+  return packed;
+}
+
 // full pipeline: LI + six general buffers A0..A5
 template <int N>
 struct Layout : LayoutT<N, 7> {
