@@ -575,6 +575,9 @@ def run_ours(args):
     # pinned host buffers NUMA-local to this rank's GPU (SYMPA_BENCH_NO_NUMA=1 switches it off for an A/B)
     # - only with several ranks: one rank keeps every host core for the CPU baseline it also times
     numa = None if (os.environ.get("SYMPA_BENCH_NO_NUMA") or world == 1) else sd.bind_to_gpu_numa_node(local)
+    if os.environ.get("SYMPA_SPLIT_PATH"):          # tuning experiments only
+        from sympa_b200 import _lib
+        _lib.check(_lib.load().sympa_set_option(_lib.OPT_SPLIT_PATH, int(os.environ["SYMPA_SPLIT_PATH"])))
     if os.environ.get("SYMPA_SCATTER_PASS_MB"):     # tuning experiments only
         from sympa_b200 import _lib
         _lib.check(_lib.load().sympa_set_option(_lib.OPT_SCATTER_PASS_MB, int(os.environ["SYMPA_SCATTER_PASS_MB"])))
