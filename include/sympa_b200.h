@@ -208,6 +208,16 @@ int sympa_bounded_rows_to_upper(int n, int64_t num_rows, const double* table, do
 int sympa_bounded_rows_backward(int n, int64_t num_rows, const double* table, const double* grad_upper,
                                 double* grad_table, int overwrite, void* stream);
 
+/* Embeddings.check_all_points (sympa/embeddings.py:41-47: a Python loop over the points calling
+ * check_point_on_manifold, run once per epoch at runner.py:91) as one launch over the table: every n x n block
+ * allclose to its transpose (atol, rtol: siegel_manifold.py:123-124), then upper: det(Im z) > 0
+ * (upper_half.py:93-114); bounded: I - conj(z) z allclose to its conjugate transpose (bounded_domain.py:119-150);
+ * spd: eigenvalues > -atol (geoopt).  *result (8 bytes of device memory, written by the call) = ~0 when every row
+ * passes, else (first offending row << 8) | reason, reason 1 = not symmetric, 2 = the kind's predicate. */
+#define SYMPA_CHECK_OK 0xFFFFFFFFFFFFFFFFull
+int sympa_check_points(int kind, int n, int64_t num_rows, const double* table, double atol, double rtol,
+                       unsigned long long* result, void* stream);
+
 /* AverageDistortionLoss.calculate_loss (sympa/losses.py:10-19): loss_out (1 double, ACCUMULATED into) +=
  * sum_p |(manifold_dist_p / graph_dist_p)^2 - 1|, and its backward grad_manifold_dist_p = grad_loss *
  * sign(.) * 2 manifold_dist_p / graph_dist_p^2 (grad_loss: 1 device double) - one kernel each instead of the

@@ -44,6 +44,7 @@ EXPORTS = (
     "sympa_distortion_loss_backward",
     "sympa_bounded_rows_to_upper",
     "sympa_bounded_rows_backward",
+    "sympa_check_points",
 )
 
 _lib = None
@@ -103,6 +104,8 @@ def load():
     lib.sympa_distortion_loss_forward.argtypes = [L, P, P, P, P]
     lib.sympa_distortion_loss_backward.restype = I
     lib.sympa_distortion_loss_backward.argtypes = [L, P, P, P, P, P]
+    lib.sympa_check_points.restype = I
+    lib.sympa_check_points.argtypes = [I, I, L, P, ctypes.c_double, ctypes.c_double, P, P]
     lib.sympa_bounded_rows_to_upper.restype = I
     lib.sympa_bounded_rows_to_upper.argtypes = [I, L, P, P, P, P]
     lib.sympa_bounded_rows_backward.restype = I

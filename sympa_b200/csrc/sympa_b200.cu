@@ -531,6 +531,94 @@ static int launch_packed_scatter(int64_t num_pairs, int per_s, int64_t num_rows,
   return SYMPA_OK;
 }
 
+
+// check_all_points (sympa/embeddings.py:41-47 loops over the points in Python and calls the manifold's
+// check_point_on_manifold on each): one thread per table row evaluates the same predicate -
+//   every kind: allclose(x, x^T, atol, rtol) on each n x n block          (siegel_manifold.py:123-124)
+//   upper:      det(Im z) > 0                                              (upper_half.py:93-114)
+//   bounded:    allclose(A, A^H) for A = I - conj(z) z, torch's default tolerances  (bounded_domain.py:119-150)
+//   spd:        eigvalsh(x) > -atol, decided as "x + atol I has a Cholesky factorisation" (geoopt)
+// and the FIRST offending row wins through an atomicMin on (row << 8 | reason), which is what the reference's
+// loop reports.  Rows are read once; the arithmetic is a few hundred flops per row.
+__device__ __forceinline__ bool close_enough(double a, double b, double atol, double rtol) {
+  return fabs(a - b) <= atol + rtol * fabs(b);     // torch.allclose; false for NaN
+}
+__global__ void __launch_bounds__(128) check_points_kernel(int kind, int n, int64_t num_rows, const double* __restrict__ table,
+                                                           double atol, double rtol, unsigned long long* result) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nn = n * n;
+  const int per = (kind == SYMPA_KIND_SPD ? 1 : 2) * nn;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < num_rows; row += stride) {
+    const double* z = table + row * per;
+    int reason = 0;
+    for (int e = 0; e < per && reason == 0; ++e) {
+      const int blk = e / nn, r = e - blk * nn, i = r / n, j = r - i * n;
+      if (!close_enough(z[e], z[blk * nn + j * n + i], atol, rtol)) reason = 1;
+    }
+    if (reason == 0) {
+      double m[SYMPA_MAX_N * SYMPA_MAX_N];
+      if (kind == SYMPA_KIND_UPPER) {           // sign of det(Y): Gaussian elimination with partial pivoting
+        for (int e = 0; e < nn; ++e) m[e] = z[nn + e];
+        bool positive = true, zero = false;
+        for (int k = 0; k < n && !zero; ++k) {
+          int piv = k;
+          for (int i = k + 1; i < n; ++i)
+            if (fabs(m[i * n + k]) > fabs(m[piv * n + k])) piv = i;
+          if (piv != k) {
+            for (int j = 0; j < n; ++j) {
+              const double t = m[k * n + j];
+              m[k * n + j] = m[piv * n + j];
+              m[piv * n + j] = t;
+            }
+            positive = !positive;
+          }
+          const double d = m[k * n + k];
+          if (!(fabs(d) > 0.0)) { zero = true; break; }      // singular (or NaN): det is not > 0
+          if (d < 0.0) positive = !positive;
+          for (int i = k + 1; i < n; ++i) {
+            const double f = m[i * n + k] / d;
+            for (int j = k + 1; j < n; ++j) m[i * n + j] -= f * m[k * n + j];
+          }
+        }
+        if (zero || !positive) reason = 2;
+      } else if (kind == SYMPA_KIND_BOUNDED) {  // A = I - conj(z) z; allclose(A, A^H), rtol 1e-5, atol 1e-8
+        const double* x = z;
+        const double* y = z + nn;
+        for (int i = 0; i < n && reason == 0; ++i)
+          for (int j = 0; j <= i && reason == 0; ++j) {
+            double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;   // a = (conj(z) z)_ij, b = (conj(z) z)_ji
+            for (int k = 0; k < n; ++k) {
+              ar += x[i * n + k] * x[k * n + j] + y[i * n + k] * y[k * n + j];
+              ai += x[i * n + k] * y[k * n + j] - y[i * n + k] * x[k * n + j];
+              br += x[j * n + k] * x[k * n + i] + y[j * n + k] * y[k * n + i];
+              bi += x[j * n + k] * y[k * n + i] - y[j * n + k] * x[k * n + i];
+            }
+            const double d = (i == j) ? 1.0 : 0.0;
+            // A_ij = d - a, (A^H)_ij = conj(A_ji) = d - conj(b)
+            const double pr = d - ar, pi = -ai, qr = d - br, qi = bi;
+            const double diff = sqrt((pr - qr) * (pr - qr) + (pi - qi) * (pi - qi));
+            if (!(diff <= 1e-8 + 1e-5 * sqrt(qr * qr + qi * qi)) || !(diff <= 1e-8 + 1e-5 * sqrt(pr * pr + pi * pi))) reason = 2;
+          }
+      } else {                                  // spd: Cholesky of x + atol I on the lower triangle
+        for (int e = 0; e < nn; ++e) m[e] = z[e];
+        for (int j = 0; j < n && reason == 0; ++j) {
+          double d = m[j * n + j] + atol;
+          for (int k = 0; k < j; ++k) d -= m[j * n + k] * m[j * n + k];
+          if (!(d > 0.0)) { reason = 2; break; }
+          const double r = 1.0 / sqrt(d);
+          m[j * n + j] = d * r;
+          for (int i = j + 1; i < n; ++i) {
+            double v = m[i * n + j];
+            for (int k = 0; k < j; ++k) v -= m[i * n + k] * m[j * n + k];
+            m[i * n + j] = v * r;
+          }
+        }
+      }
+    }
+    if (reason != 0) atomicMin(result, ((unsigned long long)row << 8) | (unsigned long long)reason);
+  }
+}
+
 }  // namespace sympa
 
 using namespace sympa;
@@ -793,6 +881,17 @@ int sympa_distortion_loss_backward(int64_t num_pairs, const double* graph_dist, 
     return SYMPA_ERR_BAD_ARG;
   distortion_loss_bwd_kernel<<<grid_for(num_pairs, 256, 32), 256, 0, (cudaStream_t)stream>>>(
       num_pairs, graph_dist, manifold_dist, grad_loss, grad_manifold_dist);
+  return check_launch();
+}
+
+int sympa_check_points(int kind, int n, int64_t num_rows, const double* table, double atol, double rtol,
+                       unsigned long long* result, void* stream) {
+  if (kind < 0 || kind > 2 || n < 1 || n > SYMPA_MAX_N) return SYMPA_ERR_UNSUPPORTED;
+  if (num_rows < 0 || result == nullptr || (num_rows > 0 && table == nullptr)) return SYMPA_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(result, 0xFF, sizeof(unsigned long long), s) != cudaSuccess) return check_launch();
+  if (num_rows == 0) return SYMPA_OK;
+  check_points_kernel<<<grid_for(num_rows, 128, 16), 128, 0, s>>>(kind, n, num_rows, table, atol, rtol, result);
   return check_launch();
 }
 

@@ -43,9 +43,16 @@ class MatrixEmbeddings(nn.Module):
             self.embeds.data = self.manifold.projx(self.embeds.data)
 
     def check_all_points(self):
-        """embeddings.py:41-47 checks the points one by one in a Python loop; the same predicate is
-        evaluated batched here and the first offender reported."""
+        """embeddings.py:41-47 checks the points one by one in a Python loop; the same predicate is evaluated in one
+        kernel launch for a table on the GPU (batched torch operations for one on the CPU) and the first offender
+        reported."""
         pts = self.embeds.data
+        kind = getattr(self.manifold, "kind", None)
+        if pts.is_cuda and pts.dtype == torch.float64 and kind in ("upper", "bounded", "spd") and pts.shape[-1] <= 10:
+            # one launch over the table (sympa_check_points): same predicate, first offender, reason strings
+            from . import ops
+            ok, row, reason = ops.check_points(kind, pts)
+            return (True, None, None) if ok else (False, pts[row], reason)
         if not torch.allclose(pts, pts.transpose(-1, -2), atol=1e-5, rtol=1e-5):
             for i in range(len(pts)):
                 ok, reason = self.manifold.check_point_on_manifold(pts[i], explain=True)

@@ -83,6 +83,32 @@ def check_status(device=None, reset=True):
     return v
 
 
+CHECK_REASONS = {1: {"upper": "Matrices are not symmetric", "bounded": "Matrices are not symmetric",
+                     "spd": "`x != x.transpose` with atol={atol}, rtol={rtol}"},
+                 2: {"upper": "'x' determinant is not > 0",
+                     "bounded": "'Id - conj(Z) Z' is not hermitian (is not definite positive)",
+                     "spd": "eigenvalues of x are not all greater than 0."}}
+
+
+def check_points(kind, table, atol=1e-5, rtol=1e-5):
+    """Embeddings.check_all_points (sympa/embeddings.py:41-47) as one launch over the table: returns (True, None,
+    None) or (False, index of the first offending row, reason) with the reference's reason strings.  One host
+    synchronisation (the 8-byte verdict)."""
+    table = _require(table, "table")
+    n = table.shape[-1]
+    _check_n(n)
+    if tuple(table.shape[1:]) != _point_shape(kind, n):
+        raise ValueError(f"table must have shape (N, {_point_shape(kind, n)})")
+    with torch.cuda.device(table.device):
+        verdict = torch.empty(1, dtype=torch.int64, device=table.device)
+        _lib.check(_lib.load().sympa_check_points(_lib.KIND[kind], n, table.shape[0], _ptr(table), float(atol), float(rtol),
+                                                  _ptr(verdict), _stream()))
+        v = int(verdict.item()) & 0xFFFFFFFFFFFFFFFF
+    if v == 0xFFFFFFFFFFFFFFFF:
+        return True, None, None
+    return False, v >> 8, CHECK_REASONS[v & 0xFF][kind].format(atol=atol, rtol=rtol)
+
+
 def _require(t, name, dtype=torch.float64):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a tensor")

@@ -845,3 +845,62 @@ def test_accumulator_scatter_on_side_stream_sm_partition(sb, scatter_sms):
     assert peaks[-1] <= 1.05 * peaks[1], peaks
     torch.testing.assert_close(t.grad, ref.grad, rtol=1e-10, atol=1e-12 * ref.grad.abs().max().item())
     sb.ops.check_status()
+
+
+@pytest.mark.parametrize("kind,n", [("upper", 2), ("upper", 4), ("upper", 10), ("bounded", 3), ("bounded", 10), ("spd", 5), ("spd", 10)])
+def test_check_points_kernel_equals_reference_predicate(sb, kind, n):
+    """sympa_check_points (Embeddings.check_all_points, sympa/embeddings.py:41-47, in one launch) against the manifold's
+    own check_point_on_manifold evaluated point by point as the reference does: verdict, FIRST offending row, reason."""
+    g = torch.Generator().manual_seed(90 + n)
+    rows = 257
+    if kind == "spd":
+        table = so.spd_spread(rows, n, generator=g)
+        man = sb.SymmetricPositiveDefinite()
+    else:
+        table = so.upper_spread(rows, n, generator=g, scale=0.3)
+        if kind == "bounded":
+            table = so.to_symmetric(so.cayley_transform(table))
+        man = make_manifold(sb, kind, n, "riem")
+
+    def reference(t):
+        for i in range(len(t)):
+            ok, reason = man.check_point_on_manifold(t[i], explain=True)
+            if not ok:
+                return False, i, reason
+        return True, None, None
+
+    def both(t):
+        got = sb.ops.check_points(kind, t.cuda())
+        want = reference(t)
+        assert got == want, (got, want)
+        return got
+
+    assert both(table) == (True, None, None)
+    # an asymmetric entry beyond the tolerance in row 200 and a smaller one (inside the tolerance) in row 100
+    t = table.clone()
+    t[100, ..., 0, 1] += 5e-6 if n > 1 else 0.0
+    t[200, ..., 1, 0] += 1e-3
+    # (bounded: the in-tolerance asymmetry of row 100 already breaks the 1e-8 Hermitian test of I - conj(z) z)
+    assert both(t)[:2] == (False, 200 if kind != "bounded" else 100)
+    # the kind's own predicate fails in row 150 (and the later row 200 stays asymmetric: the FIRST one is reported)
+    if kind == "upper":
+        t[150, 1] = torch.diag(torch.tensor([-1.0] + [1.0 + 0.1 * k for k in range(n - 1)], dtype=torch.float64))   # det < 0
+    elif kind == "spd":
+        t[150] = t[150] - (torch.linalg.eigvalsh(t[150]).min() + 0.5) * torch.eye(n, dtype=torch.float64)
+    if kind != "bounded":          # (I - conj(z) z is Hermitian for every symmetric z: that predicate cannot fail alone)
+        got = both(t)
+        assert got[:2] == (False, 150) and got[2] == sb.ops.CHECK_REASONS[2][kind]
+    # NaN anywhere: not on the manifold
+    t = table.clone()
+    t[7, ..., 0, 0] = float("nan")
+    assert both(t)[:2] == (False, 7)
+    # the model-level entry point uses the kernel for a table on the GPU
+    from sympa_b200.embeddings import MatrixEmbeddings
+    emb = MatrixEmbeddings(rows, n, man).cuda()
+    with torch.no_grad():
+        emb.embeds.copy_(table)
+    assert emb.check_all_points() == (True, None, None)
+    with torch.no_grad():
+        emb.embeds[33, ..., 0, n - 1] += 1.0
+    ok, point, reason = emb.check_all_points()
+    assert not ok and reason == sb.ops.CHECK_REASONS[1][kind].format(atol=1e-5, rtol=1e-5) and torch.equal(point, emb.embeds.data[33])
