@@ -242,6 +242,15 @@ __device__ __forceinline__ void atomic_add_full(double* __restrict__ out, const 
 #define SY_STAGE_MAX_N 4
 #endif
 // 1: every lane gathers the rows of its own pair (stage_rows); 0: the warp gathers row by row, coalesced
+// matrix sizes whose saved state alone is staged (see StageCfg::kOutOnly).  OFF by default (max < min): measured with
+// 5..6 on the B200, forward+save kernel: n = 5 2.316 -> 2.310 ms per 2^21 pairs, n = 6 4.276 -> 4.404 ms - the
+// 84 STS + bulk store replace 84 STG but the kernel's queue pressure comes from its spill traffic, which stays.
+#ifndef SY_OSTAGE_MIN_N
+#define SY_OSTAGE_MIN_N 5
+#endif
+#ifndef SY_OSTAGE_MAX_N
+#define SY_OSTAGE_MAX_N 0
+#endif
 #ifndef SY_STAGE_OWN_ROWS
 #define SY_STAGE_OWN_ROWS 0
 #endif
@@ -266,6 +275,12 @@ struct StageCfg {
   __host__ __device__ static constexpr int warp_bytes(int mode) {
     return IN_BYTES + IDX_BYTES + (mode != 0 ? 32 * out_stride(mode) * 16 : 0);
   }
+  // Sizes whose rows do not fit the gather staging (n = 5, 6: 26 / 37 kB of rows per warp) still send the saved state
+  // of the forward+save kernel through shared memory and one bulk store per operand and warp (15 / 21 kB per warp):
+  // 84 STG.64 per thread at n = 6 otherwise, in a kernel whose load-store queue is full (lg_throttle 0.97 per issue).
+  static constexpr bool kOutOnly = !kOn && (N >= SY_OSTAGE_MIN_N) && (N <= SY_OSTAGE_MAX_N) && (N <= reg_max_n(KIND)) &&
+                                   (KIND != kSpd) && (state_doubles(KIND, N) % 2 == 0);
+  static constexpr int OUT_ONLY_BYTES = 32 * 2 * state_doubles(KIND, N) * 8;
 };
 
 // (no "memory" clobber: the statement neither reads nor writes anything the compiler knows about before the
@@ -453,6 +468,11 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
   unsigned char* st_out = nullptr;             // [32 point slots]  unit gradients on their way out
   longlong2* st_idx = nullptr;                 // [2][32]           index pairs, two generations
   unsigned bad_next = 0u;                      // lanes whose staged (next) index pair was rejected
+  constexpr bool OSTAGE = S::kOutOnly && MODE == kModeFwdSave;
+  if (OSTAGE) {
+    extern __shared__ __align__(16) unsigned char sy_stage_smem[];
+    st_out = sy_stage_smem + (threadIdx.x >> 5) * S::OUT_ONLY_BYTES;
+  }
   if (STAGE) {
     extern __shared__ __align__(16) unsigned char sy_stage_smem[];
     unsigned char* wb = sy_stage_smem + (threadIdx.x >> 5) * S::warp_bytes(MODE);
@@ -598,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
       for (int k = 0; k < N; ++k) a.vvd_out[p * N + k] = vs[k];
     }
     if (STAGE) cp_async_wait_all();   // next iteration's rows and indices (issued at the top of this one): long done
-    if (STAGE && MODE == kModeFwdSave) {
+    if ((STAGE || OSTAGE) && MODE == kModeFwdSave) {
       // unit gradients -> the warp's two contiguous blocks -> one bulk store per operand into the saved state
       // (zeros for a pair whose indices were rejected; the tail is cut off by the byte count)
       constexpr int PS = state_doubles(KIND, N);
@@ -687,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, (N <= reg_max_n(KIND) && N >= 3)
     }
   }
   if (STAGE) cp_async_wait_all();
-  if (STAGE && MODE == kModeFwdSave && lane == 0) bulk_wait_all();
+  if ((STAGE || OSTAGE) && MODE == kModeFwdSave && lane == 0) bulk_wait_all();
   if (MODE == kModeStep) {
     loss_acc = warp_sum(loss_acc);
     gscale_acc = warp_sum(gscale_acc);
@@ -710,6 +730,7 @@ template <int N, int KIND, int MODE>
 static int launch_one(const PairArgs& a, cudaStream_t s) {
   int smem = 0;
   if (StageCfg<N, KIND>::kOn) smem = (kThreads / 32) * StageCfg<N, KIND>::warp_bytes(MODE);
+  if (StageCfg<N, KIND>::kOutOnly && MODE == kModeFwdSave) smem = (kThreads / 32) * StageCfg<N, KIND>::OUT_ONLY_BYTES;
   static bool configured[64] = {};  // per instantiation and device (the attribute is per function per device)
   static int resident[64] = {};     // CTAs of this instantiation that fit on one SM
   int dev = 0;
