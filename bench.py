@@ -785,21 +785,28 @@ def cfg4_step(kind, n, metric, dev, world, rank, rows=1 << 20, global_pairs=1 <<
     from sympa_b200 import ops
     lr = 1e-3 * world
 
+    # several calls per step accumulate in one packed gradient table (expanded - and all-reduced - once per step)
+    acc = man.table_grad_accumulator(table) if n_chunks > 1 else None
+
     def step():
         table.grad = None
         total = torch.zeros((), dtype=torch.float64, device=dev)
         in_backward = world > 1 and n_chunks == 1 and not owner_computes
         for c in range(n_chunks):
             sl = slice(c * chunk, (c + 1) * chunk)
-            d = man.dist_from_table(table, idx[sl], sync_grad=in_backward)
+            if acc is not None and c == n_chunks - 1:
+                acc.last_chunk()
+            d = man.dist_from_table(table, idx[sl], sync_grad=in_backward, accumulator=acc)
             loss = loss_fn.calculate_loss(gd[sl], d)
             loss.backward()
             total += loss.detach()
+        if acc is not None:
+            acc.finish(sync_grad=world > 1 and not owner_computes)
         if owner_computes and world > 1:
             # reduce-scatter by row owner, fused update of the owned rows, all-gather
             sd.sharded_rsgd_step(table, lr, lambda t, g, s: ops.rsgd_step(kind, t, g.contiguous(), s))
             return total
-        if world > 1 and not in_backward:
+        if world > 1 and not in_backward and acc is None:
             sd.allreduce_gradients([table.grad], average=True)
         opt.step()
         return total
