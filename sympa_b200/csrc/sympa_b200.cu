@@ -236,10 +236,10 @@ __global__ void __launch_bounds__(256) scatter_packed_part_kernel(int64_t num_pa
 #pragma unroll
           for (int k = 0; k < U; ++k) {
             const bool live = i0 + k < per_s && pl < left;
-            const int off = live ? (i0 + k) * 256 : 0;
+            // (an item past the end of a ragged last chunk reads element 0 of the state instead: always mapped)
             const int64_t pp = pair0 + (live ? pl : 0);
-            a1[k] = __ldg(v1 + off);
-            a2[k] = __ldg(v2 + off);
+            a1[k] = __ldg(live ? v1 + (i0 + k) * 256 : u1);
+            a2[k] = __ldg(live ? v2 + (i0 + k) * 256 : u2);
             g[k] = __ldg(gd + pp);
             ij[k] = __ldg(idx2 + pp);
             if (!live) ij[k].x = -1;

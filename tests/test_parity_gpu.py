@@ -3,6 +3,8 @@ vectors of the unmodified reference.  Tolerances (BASELINE.json north_star, SURV
   dist / vvd:  1e-9 relative (float64)
   gradients:   sym(grad) within 1e-6 max|g| for n <= 6, 1e-5 max|g| for n = 10 (the reference's own
                autograd noise is 1e-10 .. 3e-6 there)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -842,7 +844,8 @@ def test_accumulator_scatter_on_side_stream_sm_partition(sb, scatter_sms):
         acc.finish()
         peaks.append(torch.cuda.max_memory_allocated() - base)
     torch.cuda.synchronize()
-    assert peaks[-1] <= 1.05 * peaks[1], peaks
+    if not os.environ.get("SYMPA_UNDER_SANITIZER"):     # (compute-sanitizer keeps freed blocks accounted: measured there, not here)
+        assert peaks[-1] <= 1.05 * peaks[1], peaks
     torch.testing.assert_close(t.grad, ref.grad, rtol=1e-10, atol=1e-12 * ref.grad.abs().max().item())
     sb.ops.check_status()
 
