@@ -368,10 +368,9 @@ SY_HD unsigned rotate_columns(double* pr, double* pi, double* qr, double* qi, do
   return conv;
 }
 
-// Register-resident one-sided Jacobi in the Brent-Luk systolic ordering: lane g of a group holds a
-// "top" and a "bottom" column; every round each lane rotates its own pair, then the columns move
-// one lane along the ring (top row to the right, bottom row to the left, lane 0's top fixed), which
-// visits every pair once per NP - 1 rounds.  The columns never touch shared memory between the
+// Register-resident one-sided Jacobi in the one-directional ring ordering (ring_send_masks): lane g of a group
+// holds a "top" and a "bottom" column; every round each lane rotates its own pair, then passes one of the two to
+// its right neighbour, which visits every pair once per NP - 1 rounds.  The columns never touch shared memory between the
 // initial load and the final store (the shared-memory version below moved both columns of every
 // pair through shared memory every round and was bound by bank-conflicted LDS/STS wavefronts).
 // An odd n gets a zero padding column, which no rotation ever changes.  Columns carry their index so
@@ -404,37 +403,36 @@ inline int jacobi_ring_host(int G, double* gr, double* gi) {
     for (int r = 0; r < NP - 1; ++r) {
       for (int g = 0; g < G; ++g) conv |= rotate_columns<N, IS_REAL>(tr[g], ti[g], br[g], bi[g], &tn[g], &bn[g]);
       if (G > 1) {
-        double ntr[L::G][N], nti[L::G][N], nbr[L::G][N], nbi[L::G][N], ntn[L::G], nbn[L::G];
-        int ntid[L::G], nbid[L::G];
+        // one-directional ring: lane g passes its bottom column (bit 1: the one received last) or its top column
+        // (bit 0) to lane g + 1 and keeps the other as its top - the schedule of WarpExec::jacobi
+        const unsigned long long sched = ring_send_masks<L::G>();
+        double sr_[L::G][N], si_[L::G][N], sn_[L::G];
+        int sid_[L::G];
         for (int g = 0; g < G; ++g) {
-          // new top: lane 0 keeps its top, lane 1 takes lane 0's bottom, lane g takes lane g-1's top
-          const double* sr_ = g == 0 ? tr[0] : (g == 1 ? br[0] : tr[g - 1]);
-          const double* si_ = g == 0 ? ti[0] : (g == 1 ? bi[0] : ti[g - 1]);
-          ntid[g] = g == 0 ? tid[0] : (g == 1 ? bid[0] : tid[g - 1]);
-          ntn[g] = g == 0 ? tn[0] : (g == 1 ? bn[0] : tn[g - 1]);
-          // new bottom: lane g takes lane g+1's bottom, the last lane takes its own top
-          const double* ur_ = g == G - 1 ? tr[g] : br[g + 1];
-          const double* ui_ = g == G - 1 ? ti[g] : bi[g + 1];
-          nbid[g] = g == G - 1 ? tid[g] : bid[g + 1];
-          nbn[g] = g == G - 1 ? tn[g] : bn[g + 1];
+          const bool pass_b = ((sched >> (r * L::G + g)) & 1ull) != 0ull;
           for (int i = 0; i < N; ++i) {
-            ntr[g][i] = sr_[i];
-            nti[g][i] = si_[i];
-            nbr[g][i] = ur_[i];
-            nbi[g][i] = ui_[i];
+            sr_[g][i] = pass_b ? br[g][i] : tr[g][i];
+            si_[g][i] = pass_b ? bi[g][i] : ti[g][i];
+            if (!pass_b) {
+              tr[g][i] = br[g][i];
+              ti[g][i] = bi[g][i];
+            }
+          }
+          sn_[g] = pass_b ? bn[g] : tn[g];
+          sid_[g] = pass_b ? bid[g] : tid[g];
+          if (!pass_b) {
+            tn[g] = bn[g];
+            tid[g] = bid[g];
           }
         }
         for (int g = 0; g < G; ++g) {
-          tid[g] = ntid[g];
-          bid[g] = nbid[g];
-          tn[g] = ntn[g];
-          bn[g] = nbn[g];
+          const int src = g == 0 ? G - 1 : g - 1;
           for (int i = 0; i < N; ++i) {
-            tr[g][i] = ntr[g][i];
-            ti[g][i] = nti[g][i];
-            br[g][i] = nbr[g][i];
-            bi[g][i] = nbi[g][i];
+            br[g][i] = sr_[src][i];
+            bi[g][i] = si_[src][i];
           }
+          bn[g] = sn_[src];
+          bid[g] = sid_[src];
         }
       }
     }

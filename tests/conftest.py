@@ -78,5 +78,10 @@ def hostcheck():
         assert projected >= 0
         return t, int(projected)
 
+    def ring_send_masks(g):
+        dll.hostcheck_ring_send_masks.restype = ctypes.c_uint64
+        return int(dll.hostcheck_ring_send_masks(int(g)))
+
     run.rsgd = rsgd
+    run.ring_send_masks = ring_send_masks
     return run

@@ -250,3 +250,16 @@ extern "C" int64_t hostcheck_rsgd(int variant, int kind, int n, int64_t rows, do
   }
   return -1;
 }
+
+// the tabulated one-directional ring schedule of the register-resident Jacobi (coop::ring_send_masks), for the
+// combinatorial test in tests/test_hostcheck.py
+extern "C" unsigned long long hostcheck_ring_send_masks(int g) {
+  switch (g) {
+    case 1: return sympa::coop::ring_send_masks<1>();
+    case 2: return sympa::coop::ring_send_masks<2>();
+    case 3: return sympa::coop::ring_send_masks<3>();
+    case 4: return sympa::coop::ring_send_masks<4>();
+    case 5: return sympa::coop::ring_send_masks<5>();
+  }
+  return ~0ull;
+}

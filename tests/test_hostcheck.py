@@ -152,3 +152,34 @@ def test_clamped_and_nearly_coincident_pairs(hostcheck, n):
                     # d ~ 1e-9: absolute agreement at the level of the reference's own round-off
                     np.testing.assert_allclose(d, d_ref.numpy(), rtol=1e-4, atol=1e-13)
                     assert np.all(np.isfinite(g1)) and np.all(np.isfinite(g2))
+
+
+@pytest.mark.parametrize("G", [2, 3, 4, 5])
+def test_one_directional_ring_schedule_meets_every_pair_once_per_sweep(hostcheck, G):
+    """coop::ring_send_masks (the schedule WarpExec::jacobi runs on the GPU for n = 2G - 1, 2G): G lanes hold two columns,
+    after every round each lane passes ONE of them to its right neighbour.  Simulated here from the packed table the
+    kernels use: in the N - 1 rounds of a sweep all N (N - 1) / 2 column pairs meet exactly once, from any starting
+    arrangement, sweep after sweep, and no pair meets in two consecutive rounds across a sweep boundary."""
+    packed = hostcheck.ring_send_masks(G)
+    N = 2 * G
+    rng = np.random.default_rng(G)
+    for trial in range(5):
+        labels = rng.permutation(N)
+        kept = [int(labels[2 * g]) for g in range(G)]        # slot 0 of lane g ("top")
+        recv = [int(labels[2 * g + 1]) for g in range(G)]    # slot 1 ("bottom": the column received last)
+        last_round = set()
+        for sweep in range(4):
+            met = set()
+            for r in range(N - 1):
+                pairs = {(min(a, b), max(a, b)) for a, b in zip(kept, recv)}
+                assert len(pairs) == G and not (pairs & met), (G, sweep, r)
+                if r == 0:
+                    assert not (pairs & last_round)
+                met |= pairs
+                last_round = pairs
+                bits = [(packed >> (r * G + g)) & 1 for g in range(G)]
+                sent = [recv[g] if bits[g] else kept[g] for g in range(G)]
+                kept = [kept[g] if bits[g] else recv[g] for g in range(G)]
+                recv = [sent[(g - 1) % G] for g in range(G)]
+            assert len(met) == N * (N - 1) // 2
+    assert packed >> (G * (N - 1)) == 0      # nothing beyond the N - 1 masks
