@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of build variants (build/mkvariant.sh NAME "N list" "-D...") against the main library.
+# A/B of build variants (profiles/mkvariant.sh NAME "N list" "-D...") against the main library.
 # usage: bash profiles/r02_variants.sh "name|bench args" ...   (every variant .so under build/variants runs every spec)
 cd $GRAFT_REPO_ROOT
 show() { python -c "
