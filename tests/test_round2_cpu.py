@@ -89,3 +89,16 @@ def test_bounded_route_choice_is_rank_invariant_under_sync_grad():
     assert all(same for same, _ in r0[0]) and all(same for same, _ in r1[0])
     assert [v for _, v in r0[0]] == [True, True, True, False]      # bounded by rows up to n = 10 (ops.BOUNDED_BY_ROWS_MAX_N)
     assert (r0[1], r1[1]) == (True, False)       # single-process rule: 2 * pairs >= rows
+
+
+def test_numa_binding_helper_parses_cpulists_and_is_inert_without_a_gpu():
+    """distributed.bind_to_gpu_numa_node: sysfs cpulist syntax, and no change of the affinity when there is no GPU
+    (or no readable topology) - the bench calls it unconditionally for N > 1."""
+    sys.path.insert(0, ROOT)
+    from sympa_b200 import distributed as sd
+    assert sd._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sd._parse_cpulist("5") == {5} and sd._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert sd.bind_to_gpu_numa_node(0) is None
+        assert os.sched_getaffinity(0) == before
